@@ -1,0 +1,110 @@
+/*
+ * panfusion_b200 — C ABI of the B200 (sm_100a) denoise hot path of PanFusion.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream (cudaStream_t passed as void*).
+ * The caller (PyTorch on the host side) owns every buffer; the library keeps no hidden state except a
+ * thread-local error string. All functions return 0 on success or a negative PF_ERR_* code; launches are
+ * asynchronous on the given stream and CUDA-graph capturable (no allocation, no host sync inside).
+ *
+ * Each declaration cites the reference interface (file:line under the upstream repo) it replaces.
+ * Tensors are row-major; "tokens" layout means [N*H*W, C] channels-last, "NCHW" is the reference's layout.
+ */
+#ifndef PANFUSION_B200_H
+#define PANFUSION_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_OK 0
+#define PF_ERR_INVALID (-1)     /* bad argument (message in pf_last_error) */
+#define PF_ERR_CUDA (-2)        /* CUDA runtime / driver failure */
+#define PF_ERR_UNSUPPORTED (-3) /* shape / dtype not supported by the sm_100a kernels */
+
+typedef enum { PF_F32 = 0, PF_F16 = 1, PF_BF16 = 2 } pf_dtype;
+
+/* error convention: reference raises Python exceptions (utils/pano.py:85,
+ * external/Perspective_and_Equirectangular/utils.py:15); here: return code + message. */
+const char* pf_last_error(void);
+int pf_version(void);
+/* returns 0 iff the current device is compute capability 10.x (B200); the library has no other path */
+int pf_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Spherical resampling (K1/K2): external/Perspective_and_Equirectangular/e2p.py:54-76, p2e.py:52-77
+ * The sampling grid is computed in-kernel (fp64 per output pixel) from the camera record; no grid is
+ * stored. Sampling follows kornia.remap -> F.grid_sample(align_corners=True, padding_mode='zeros').
+ *
+ * Camera record: PF_CAM_DOUBLES doubles, device memory, one per batch element (cam_stride = 1) or a single
+ * record broadcast over the batch (cam_stride = 0):
+ *   [0:9)  R1  row-major   (e2p: Rodrigues(z * rad(theta));   p2e: inv(R1))
+ *   [9:18) R2  row-major   (e2p: Rodrigues(R1 y * rad(-phi)); p2e: inv(R2))
+ *   [18] w_len = tan(rad(wfov/2))   [19] h_len = tan(rad(hfov/2))
+ * mode: 0 = bilinear, 1 = nearest (round-half-even).
+ * ------------------------------------------------------------------------------------------------ */
+#define PF_CAM_DOUBLES 20
+
+/* e2p(e_img[B,C,He,We]) -> [B,C,h,w]   (e2p.py:54-76; grid math e2p.py:9-51) */
+int pf_e2p(const void* src, void* dst, int dtype, int B, int C, int He, int We, int h, int w,
+           const double* cams, int cam_stride, int mode, void* stream);
+
+/* p2e(p_img[B,C,hp,wp]) -> equi[B,C,He,We] (already multiplied by mask), mask[B,1,He,We] uint8 (may be NULL)
+ * (p2e.py:52-77; grid math p2e.py:9-49) */
+int pf_p2e(const void* src, void* dst, uint8_t* mask, int dtype, int B, int C, int hp, int wp, int He, int We,
+           const double* cams, int cam_stride, int mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tap-GEMM (tcgen05 / TMEM / TMA): the one dense-contraction engine behind nn.Linear (K8, K10) and the
+ * 3x3 / 1x1 convolutions (K9, K11) of the UNet walk in models/pano/MVGenModel.py:85-295.
+ *
+ *   acc[m, n] = sum_{t < num_taps} sum_{k < Kc} A[m + tap_off[t], k] * B[n, t*Kc + k]      (fp32 accumulate)
+ *   v        = act(acc + bias[n] + rowbias[group(m), n])           (GEGLU: v = a * gelu(g), see below)
+ *   out[row(m), n] = v + residual[row(m), n]
+ *
+ * A is a row-major [a_rows, a_ld] 16-bit matrix (rows outside [0, a_rows) read as zero), B the packed
+ * weight [N, num_taps*Kc]. A 3x3 convolution is 9 taps over a zero-haloed channels-last image
+ * ("padded-flat" layout); the M-space -> output-row map drops halo rows:
+ *   map_mode 0: row(m) = m, group(m) = m / rows_per_group
+ *   map_mode 1: m -> (img, i, j) with i = (m / Wm) % Hm, j = m % Wm; valid iff i0 <= i < i0+Hout and
+ *               j0 <= j < j0+Wout; row(m) = (img*Hout + i-i0)*Wout + (j-j0); group(m) = img
+ * act: PF_ACT_GEGLU expects B (and bias) packed so that every block_n-wide column tile holds block_n/2 value
+ * columns followed by their block_n/2 gate columns; it writes N/2 output columns.
+ * Constraints: Kc % 64 == 0, N % block_n == 0, block_n in {64,128,160,256}, a_ld/b_ld % 8 == 0.
+ * ------------------------------------------------------------------------------------------------ */
+enum { PF_ACT_NONE = 0, PF_ACT_SILU = 1, PF_ACT_GELU = 2, PF_ACT_GEGLU = 3 };
+#define PF_MAX_TAPS 16
+
+typedef struct pf_gemm_args {
+  const void* A;
+  int64_t a_rows;
+  int32_t a_ld;
+  const void* B;
+  int32_t b_ld;
+  int32_t dtype; /* PF_F16 | PF_BF16 (A and B) */
+  int32_t M, N, Kc, num_taps;
+  int32_t tap_off[PF_MAX_TAPS];
+  int32_t block_n; /* 0 = auto */
+  void* out;
+  int32_t out_ld;
+  int32_t out_dtype; /* PF_F32 or same as dtype */
+  const float* bias;
+  const float* rowbias;
+  int32_t rowbias_ld;
+  int32_t rows_per_group;
+  const void* residual;
+  int32_t res_ld;
+  int32_t res_dtype;
+  int32_t act;
+  int32_t map_mode, Hm, Wm, i0, j0, Hout, Wout;
+} pf_gemm_args;
+
+int pf_gemm_taps(const pf_gemm_args* args, void* stream);
+/* block_n the auto-tuner would pick for this N (used by the host-side weight packer for GEGLU) */
+int pf_gemm_pick_block_n(int N, int act);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANFUSION_B200_H */

@@ -1,0 +1,98 @@
+"""ctypes binding of the C-ABI library (include/panfusion_b200.h).
+
+There is no fallback: if the shared object is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+PF_F32, PF_F16, PF_BF16 = 0, 1, 2
+PF_ACT_NONE, PF_ACT_SILU, PF_ACT_GELU, PF_ACT_GEGLU = 0, 1, 2, 3
+PF_MAX_TAPS = 16
+PF_CAM_DOUBLES = 20
+
+_DTYPES = {torch.float32: PF_F32, torch.float16: PF_F16, torch.bfloat16: PF_BF16}
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpanfusion_b200.so"
+
+
+class PFError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("a_rows", C.c_int64), ("a_ld", C.c_int32),
+        ("B", C.c_void_p), ("b_ld", C.c_int32), ("dtype", C.c_int32),
+        ("M", C.c_int32), ("N", C.c_int32), ("Kc", C.c_int32), ("num_taps", C.c_int32),
+        ("tap_off", C.c_int32 * PF_MAX_TAPS), ("block_n", C.c_int32),
+        ("out", C.c_void_p), ("out_ld", C.c_int32), ("out_dtype", C.c_int32),
+        ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_ld", C.c_int32), ("rows_per_group", C.c_int32),
+        ("residual", C.c_void_p), ("res_ld", C.c_int32), ("res_dtype", C.c_int32),
+        ("act", C.c_int32),
+        ("map_mode", C.c_int32), ("Hm", C.c_int32), ("Wm", C.c_int32), ("i0", C.c_int32), ("j0", C.c_int32),
+        ("Hout", C.c_int32), ("Wout", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) the native library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise PFError(
+                f"{LIB_PATH} not found: build it with `python -m panfusion_b200.build` "
+                "(panfusion_b200 has no non-CUDA path)")
+        l = C.CDLL(str(LIB_PATH))
+        l.pf_last_error.restype = C.c_char_p
+        for name in EXPORTS:
+            getattr(l, name)  # AttributeError if the header and the library diverge
+        _lib = l
+    return _lib
+
+
+# every symbol include/panfusion_b200.h declares (checked by tests/test_cabi.py against the header text)
+EXPORTS = [
+    "pf_last_error", "pf_version", "pf_check_device",
+    "pf_e2p", "pf_p2e",
+    "pf_gemm_taps", "pf_gemm_pick_block_n",
+]
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().pf_last_error().decode(errors="replace")
+        if rc == -1:
+            raise ValueError(msg)
+        if rc == -3:
+            raise NotImplementedError(msg)
+        raise PFError(f"[{rc}] {msg}")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPES[dt]
+    except KeyError:
+        raise ValueError(f"unsupported dtype {dt}") from None
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise PFError("panfusion_b200 kernels need CUDA tensors (there is no CPU path)")

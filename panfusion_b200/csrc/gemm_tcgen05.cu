@@ -1,0 +1,383 @@
+// Tap-GEMM on tcgen05: TMA (SWIZZLE_128B) -> shared -> tcgen05.mma (UMMA 128 x BLOCK_N x 16, fp32 in TMEM)
+// -> tcgen05.ld epilogue. One kernel serves nn.Linear and every 1x1 / 3x3 convolution of the UNet walk
+// (reference call sites: models/pano/MVGenModel.py:85-295 through diffusers ResnetBlock2D / Transformer2DModel,
+//  models/modules/transformer.py:57-74,8-35). A convolution is a sum of `num_taps` GEMMs whose A operand is the
+// same channels-last image shifted by a constant row offset (zero-haloed "padded-flat" layout), so the im2col
+// matrix is never formed: each K-slab is one plain 2-D TMA box.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane),
+// warps 2..5 = epilogue (thread <-> accumulator row, TMEM lane quarter = warp_id % 4).
+#include "pf_common.cuh"
+
+namespace pf {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;  // 64 x 16-bit = 128 B = one swizzle row
+constexpr int GEMM_THREADS = 192;
+
+struct GemmKernelParams {
+  int M, N, num_kb, kb_per_tap;
+  int tap_off[PF_MAX_TAPS];
+  void* out;
+  int out_ld;
+  int out_f32;
+  const float* bias;
+  const float* rowbias;
+  int rowbias_ld;
+  int rows_per_group;
+  const void* residual;
+  int res_ld;
+  int res_f32;
+  int act;
+  int map_mode, Hm, Wm, i0, j0, Hout, Wout;
+};
+
+__host__ __device__ constexpr int gemm_tmem_cols(int block_n) {
+  return block_n <= 32 ? 32 : block_n <= 64 ? 64 : block_n <= 128 ? 128 : block_n <= 256 ? 256 : 512;
+}
+__host__ __device__ constexpr int gemm_stage_bytes(int block_n) {
+  return GEMM_BLOCK_M * GEMM_BLOCK_K * 2 + block_n * GEMM_BLOCK_K * 2;
+}
+__host__ __device__ constexpr int gemm_smem_bytes(int block_n, int stages) {
+  return stages * gemm_stage_bytes(block_n) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+template <int BLOCK_N, int STAGES, bool BF16>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmKernelParams p) {
+  constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+  constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = gemm_tmem_cols(BLOCK_N);
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA M=128 needs N%16==0, N<=256");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = p.N / BLOCK_N;
+  const int n_tile = blockIdx.x % n_tiles;  // n fastest: concurrent CTAs share the A tile through L2
+  const int m_tile = blockIdx.x / n_tiles;
+  const int m0 = m_tile * GEMM_BLOCK_M;
+  const int n0 = n_tile * BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        const int tap = kb / p.kb_per_tap;
+        const int kk = kb - tap * p.kb_per_tap;
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        tma_load_2d(sa, &tmA, &full_bar[s], kk * GEMM_BLOCK_K, m0 + p.tap_off[tap]);
+        tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], kb * GEMM_BLOCK_K, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BF16 ? 1 : 0, GEMM_BLOCK_M, BLOCK_N, 0, 0);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc(sa, 16, 1024, 2);
+        const uint64_t bdesc = make_smem_desc(sa + A_BYTES, 16, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+          // +32 B per UMMA_K step inside the 128 B swizzle row => +2 in the (addr >> 4) field
+          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ------------------------------ epilogue -----------------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    bool valid = m < p.M;
+    long long orow = m;
+    int group = 0;
+    if (p.map_mode == 1) {
+      const int hw = p.Hm * p.Wm;
+      const int img = m / hw;
+      const int r = m - img * hw;
+      const int i = r / p.Wm;
+      const int j = r - i * p.Wm;
+      valid = valid && i >= p.i0 && i < p.i0 + p.Hout && j >= p.j0 && j < p.j0 + p.Wout;
+      orow = ((long long)img * p.Hout + (i - p.i0)) * p.Wout + (j - p.j0);
+      group = img;
+    } else if (p.rowbias) {
+      group = m / p.rows_per_group;
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr_row = tmem_base + (uint32_t(q * 32) << 16);
+
+    constexpr bool kDummy = false;
+    (void)kDummy;
+    if (p.act == PF_ACT_GEGLU) {
+      constexpr int HALF = BLOCK_N / 2;
+      const int on0 = n_tile * HALF;
+      if constexpr (HALF % 16 == 0) {
+#pragma unroll 1
+        for (int c = 0; c < HALF; c += 16) {
+          uint32_t va[16], vg[16];
+          tmem_ld16(taddr_row + c, va);
+          tmem_ld16(taddr_row + HALF + c, vg);
+          tmem_ld_wait();
+          if (valid) {
+            float o[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              float a = __uint_as_float(va[e]);
+              float g = __uint_as_float(vg[e]);
+              if (p.bias) {
+                a += __ldg(p.bias + n0 + c + e);
+                g += __ldg(p.bias + n0 + HALF + c + e);
+              }
+              o[e] = a * gelu_erf_f(g);
+            }
+            if (p.out_f32) {
+              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.out_ld + on0 + c);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + orow * p.out_ld + on0 + c);
+              dst[0] = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]), pack2<BF16>(o[4], o[5]),
+                                  pack2<BF16>(o[6], o[7]));
+              dst[1] = make_uint4(pack2<BF16>(o[8], o[9]), pack2<BF16>(o[10], o[11]), pack2<BF16>(o[12], o[13]),
+                                  pack2<BF16>(o[14], o[15]));
+            }
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr_row + c, v);
+        tmem_ld_wait();
+        if (valid) {
+          float o[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[e]);
+          if (p.bias) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] += __ldg(p.bias + n0 + c + e);
+          }
+          if (p.rowbias) {
+            const float* rb = p.rowbias + (long long)group * p.rowbias_ld + n0 + c;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] += __ldg(rb + e);
+          }
+          if (p.act == PF_ACT_SILU) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = silu_f(o[e]);
+          } else if (p.act == PF_ACT_GELU) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = gelu_erf_f(o[e]);
+          }
+          if (p.residual) {
+            if (p.res_f32) {
+              const float4* r4 =
+                  reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + orow * p.res_ld + n0 + c);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float4 t = r4[e];
+                o[4 * e] += t.x;
+                o[4 * e + 1] += t.y;
+                o[4 * e + 2] += t.z;
+                o[4 * e + 3] += t.w;
+              }
+            } else {
+              const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.residual) +
+                                                               orow * p.res_ld + n0 + c);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint4 t = r4[h];
+                float2 f;
+                f = unpack2<BF16>(t.x); o[8 * h + 0] += f.x; o[8 * h + 1] += f.y;
+                f = unpack2<BF16>(t.y); o[8 * h + 2] += f.x; o[8 * h + 3] += f.y;
+                f = unpack2<BF16>(t.z); o[8 * h + 4] += f.x; o[8 * h + 5] += f.y;
+                f = unpack2<BF16>(t.w); o[8 * h + 6] += f.x; o[8 * h + 7] += f.y;
+              }
+            }
+          }
+          if (p.out_f32) {
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.out_ld + n0 + c);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + orow * p.out_ld + n0 + c);
+            dst[0] = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]), pack2<BF16>(o[4], o[5]),
+                                pack2<BF16>(o[6], o[7]));
+            dst[1] = make_uint4(pack2<BF16>(o[8], o[9]), pack2<BF16>(o[10], o[11]), pack2<BF16>(o[12], o[13]),
+                                pack2<BF16>(o[14], o[15]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_gemm(const pf_gemm_args* a, const GemmKernelParams& kp, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)a->Kc, (uint64_t)a->a_rows};
+    uint64_t str[1] = {(uint64_t)a->a_ld * 2};
+    uint32_t box[2] = {GEMM_BLOCK_K, GEMM_BLOCK_M};
+    int rc = make_tmap(&tmA, a->dtype, 2, a->A, dims, str, box, 128);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->Kc * a->num_taps, (uint64_t)a->N};
+    uint64_t str[1] = {(uint64_t)a->b_ld * 2};
+    uint32_t box[2] = {GEMM_BLOCK_K, (uint32_t)BLOCK_N};
+    int rc = make_tmap(&tmB, a->dtype, 2, a->B, dims, str, box, 128);
+    if (rc) return rc;
+  }
+  constexpr int SMEM = gemm_smem_bytes(BLOCK_N, STAGES);
+  const int m_tiles = (a->M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int grid = m_tiles * (a->N / BLOCK_N);
+  if (a->dtype == PF_BF16) {
+    auto kern = gemm_taps_kernel<BLOCK_N, STAGES, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM),
+                          "cudaFuncSetAttribute(gemm)");
+      if (rc) return rc;
+      attr_set = true;
+    }
+    kern<<<grid, GEMM_THREADS, SMEM, st>>>(tmA, tmB, kp);
+  } else {
+    auto kern = gemm_taps_kernel<BLOCK_N, STAGES, false>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM),
+                          "cudaFuncSetAttribute(gemm)");
+      if (rc) return rc;
+      attr_set = true;
+    }
+    kern<<<grid, GEMM_THREADS, SMEM, st>>>(tmA, tmB, kp);
+  }
+  PF_CHECK_LAUNCH("gemm_taps_kernel");
+  return PF_OK;
+}
+
+}  // namespace pf
+
+extern "C" int pf_gemm_pick_block_n(int N, int act) {
+  (void)act;
+  if (N % 160 == 0) return 160;
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  return 0;
+}
+
+extern "C" int pf_gemm_taps(const pf_gemm_args* a, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(a != nullptr, "pf_gemm_taps: null args");
+  PF_CHECK_ARG(a->dtype == PF_BF16 || a->dtype == PF_F16, "pf_gemm_taps: dtype must be PF_F16 or PF_BF16");
+  PF_CHECK_ARG(a->A && a->B && a->out, "pf_gemm_taps: null operand");
+  PF_CHECK_ARG(a->M > 0 && a->N > 0 && a->Kc > 0, "pf_gemm_taps: empty problem M=%d N=%d Kc=%d", a->M, a->N, a->Kc);
+  PF_CHECK_ARG(a->Kc % GEMM_BLOCK_K == 0, "pf_gemm_taps: Kc=%d must be a multiple of 64", a->Kc);
+  PF_CHECK_ARG(a->num_taps >= 1 && a->num_taps <= PF_MAX_TAPS, "pf_gemm_taps: num_taps=%d out of range", a->num_taps);
+  PF_CHECK_ARG(a->a_ld % 8 == 0 && a->b_ld % 8 == 0 && a->a_ld >= a->Kc && a->b_ld >= a->Kc * a->num_taps,
+               "pf_gemm_taps: bad leading dims a_ld=%d b_ld=%d", a->a_ld, a->b_ld);
+  PF_CHECK_ARG((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
+               "pf_gemm_taps: operands must be 16-byte aligned");
+  PF_CHECK_ARG(a->out_dtype == PF_F32 || a->out_dtype == a->dtype, "pf_gemm_taps: out_dtype must be f32 or dtype");
+  PF_CHECK_ARG(!a->residual || a->res_dtype == PF_F32 || a->res_dtype == a->dtype,
+               "pf_gemm_taps: res_dtype must be f32 or dtype");
+  PF_CHECK_ARG(a->act >= PF_ACT_NONE && a->act <= PF_ACT_GEGLU, "pf_gemm_taps: unknown act %d", a->act);
+  int bn = a->block_n ? a->block_n : pf_gemm_pick_block_n(a->N, a->act);
+  PF_CHECK_ARG(bn == 64 || bn == 128 || bn == 160 || bn == 256, "pf_gemm_taps: unsupported block_n %d (N=%d)", bn, a->N);
+  PF_CHECK_ARG(a->N % bn == 0, "pf_gemm_taps: N=%d not a multiple of block_n=%d", a->N, bn);
+  const int n_out = a->act == PF_ACT_GEGLU ? a->N / 2 : a->N;
+  PF_CHECK_ARG(a->out_ld % 8 == 0 && a->out_ld >= n_out, "pf_gemm_taps: bad out_ld %d", a->out_ld);
+  PF_CHECK_ARG(!a->residual || (a->res_ld % 8 == 0 && a->res_ld >= n_out), "pf_gemm_taps: bad res_ld %d", a->res_ld);
+  PF_CHECK_ARG(!(a->act == PF_ACT_GEGLU && (a->residual || a->rowbias)),
+               "pf_gemm_taps: GEGLU epilogue takes no residual/rowbias");
+  if (a->map_mode == 1) {
+    PF_CHECK_ARG(a->Hm > 0 && a->Wm > 0 && a->Hout > 0 && a->Wout > 0 && a->M % (a->Hm * a->Wm) == 0,
+                 "pf_gemm_taps: bad image map Hm=%d Wm=%d M=%d", a->Hm, a->Wm, a->M);
+  } else {
+    PF_CHECK_ARG(a->map_mode == 0, "pf_gemm_taps: unknown map_mode %d", a->map_mode);
+    PF_CHECK_ARG(!a->rowbias || a->rows_per_group > 0, "pf_gemm_taps: rowbias needs rows_per_group");
+  }
+
+  GemmKernelParams kp;
+  kp.M = a->M;
+  kp.N = a->N;
+  kp.kb_per_tap = a->Kc / GEMM_BLOCK_K;
+  kp.num_kb = kp.kb_per_tap * a->num_taps;
+  for (int t = 0; t < PF_MAX_TAPS; ++t) kp.tap_off[t] = t < a->num_taps ? a->tap_off[t] : 0;
+  kp.out = a->out;
+  kp.out_ld = a->out_ld;
+  kp.out_f32 = a->out_dtype == PF_F32;
+  kp.bias = a->bias;
+  kp.rowbias = a->rowbias;
+  kp.rowbias_ld = a->rowbias_ld;
+  kp.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
+  kp.residual = a->residual;
+  kp.res_ld = a->res_ld;
+  kp.res_f32 = a->res_dtype == PF_F32;
+  kp.act = a->act;
+  kp.map_mode = a->map_mode;
+  kp.Hm = a->Hm;
+  kp.Wm = a->Wm;
+  kp.i0 = a->i0;
+  kp.j0 = a->j0;
+  kp.Hout = a->Hout;
+  kp.Wout = a->Wout;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 64: return launch_gemm<64, 4>(a, kp, st);
+    case 128: return launch_gemm<128, 3>(a, kp, st);
+    case 160: return launch_gemm<160, 3>(a, kp, st);
+    case 256: return launch_gemm<256, 2>(a, kp, st);
+  }
+  return PF_ERR_UNSUPPORTED;
+}

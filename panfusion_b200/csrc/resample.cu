@@ -1,0 +1,347 @@
+// Spherical resampling kernels: equirect -> perspective (e2p) and perspective -> equirect (p2e).
+// Reference: external/Perspective_and_Equirectangular/e2p.py:9-76, p2e.py:9-77 (grid built on the CPU in
+// float64 numpy per camera, uploaded, then kornia.remap == F.grid_sample(align_corners=True, zeros)).
+// Here the grid is evaluated in-kernel in fp64 per output pixel (amortised over the channel loop), rounded to
+// fp32 exactly where the reference rounds (`.type(e_img.dtype)`), and pushed through the same fp32
+// normalise / un-normalise round trip as kornia + ATen so the bilinear taps agree with the oracle.
+//
+// Two variants per direction:
+//   * staged  : the source planes of a channel group are brought into shared memory with 1-D bulk async copies
+//               (cp.async.bulk, mbarrier completion), double-buffered; taps are computed once per CTA and reused
+//               for every channel. Used when a source plane fits in shared memory (all EPPA / latent shapes).
+//   * direct  : gathers straight from global memory (L2) — any plane size (pixel-space panoramas).
+#include <math.h>
+
+#include "pf_common.cuh"
+
+namespace pf {
+
+struct Taps {
+  int idx[4];   // linear source index (y*W+x) or -1 when out of bounds / masked
+  float w[4];
+};
+
+// kornia.geometry.transform.remap -> normalize_pixel_coordinates (factor = 2/(size-1), fp32) followed by
+// ATen grid_sampler_unnormalize(align_corners=True): ((g + 1) / 2) * (size - 1), all in fp32, no FMA contraction.
+__device__ __forceinline__ float roundtrip_coord(float pix, int size) {
+  const float factor = __fdiv_rn(2.0f, fmaxf(float(size - 1), 1e-14f));
+  const float g = __fsub_rn(__fmul_rn(factor, pix), 1.0f);
+  return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.0f), 2.0f), float(size - 1));
+}
+
+// ATen CPU GridSamplerKernel bilinear: w = x - floor(x), e = 1 - w, n = y - floor(y), s = 1 - n;
+// nw = s*e, ne = s*w, sw = n*e, se = n*w; out-of-range taps are dropped (padding_mode='zeros').
+__device__ __forceinline__ void make_taps(float px, float py, int H, int W, int mode, bool live, Taps& t) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    t.idx[k] = -1;
+    t.w[k] = 0.f;
+  }
+  if (!live) return;
+  const float x = roundtrip_coord(px, W);
+  const float y = roundtrip_coord(py, H);
+  if (mode == 1) {  // nearest: round half to even
+    const float xr = nearbyintf(x), yr = nearbyintf(y);
+    if (xr >= 0.f && xr <= float(W - 1) && yr >= 0.f && yr <= float(H - 1)) {
+      t.idx[0] = int(yr) * W + int(xr);
+      t.w[0] = 1.f;
+    }
+    return;
+  }
+  const float xw = floorf(x), yn = floorf(y);
+  const float w = __fsub_rn(x, xw), e = __fsub_rn(1.0f, w);
+  const float n = __fsub_rn(y, yn), s = __fsub_rn(1.0f, n);
+  // NaN coordinates compare false everywhere -> all taps dropped (matches the masked gathers)
+  const bool x0 = xw >= 0.f && xw <= float(W - 1);
+  const bool x1 = (xw + 1.f) >= 0.f && (xw + 1.f) <= float(W - 1);
+  const bool y0 = yn >= 0.f && yn <= float(H - 1);
+  const bool y1 = (yn + 1.f) >= 0.f && (yn + 1.f) <= float(H - 1);
+  const int ix = int(xw), iy = int(yn);
+  if (x0 && y0) { t.idx[0] = iy * W + ix;           t.w[0] = __fmul_rn(s, e); }
+  if (x1 && y0) { t.idx[1] = iy * W + ix + 1;       t.w[1] = __fmul_rn(s, w); }
+  if (x0 && y1) { t.idx[2] = (iy + 1) * W + ix;     t.w[2] = __fmul_rn(n, e); }
+  if (x1 && y1) { t.idx[3] = (iy + 1) * W + ix + 1; t.w[3] = __fmul_rn(n, w); }
+}
+
+// numpy.linspace(start, stop, n)[i]: i*step + start with step = (stop-start)/(n-1); last element pinned to stop.
+__device__ __forceinline__ double np_linspace(double start, double stop, int n, int i) {
+  if (n == 1) return start;
+  if (i == n - 1) return stop;
+  const double step = (stop - start) / double(n - 1);
+  return double(i) * step + start;
+}
+
+__device__ __forceinline__ void rot3(const double* R, double x, double y, double z, double& ox, double& oy,
+                                     double& oz) {
+  ox = R[0] * x + R[1] * y + R[2] * z;
+  oy = R[3] * x + R[4] * y + R[5] * z;
+  oz = R[6] * x + R[7] * y + R[8] * z;
+}
+
+// e2p.py:9-51 (map_pers_coords_to_equi + map_pers_pix_to_equi): pixel coords in the equirect image
+__device__ __forceinline__ void e2p_grid(const double* cam, int r, int c, int h, int w, int He, int We, float& px,
+                                         float& py, double* lon_out = nullptr, double* lat_out = nullptr) {
+  const double w_len = cam[18], h_len = cam[19];
+  const double ym = np_linspace(-w_len, w_len, w, c);
+  const double zm = -np_linspace(-h_len, h_len, h, r);
+  const double D = sqrt(1.0 + ym * ym + zm * zm);
+  const double vx = 1.0 / D, vy = ym / D, vz = zm / D;
+  double ax, ay, az, bx, by, bz;
+  rot3(cam, vx, vy, vz, ax, ay, az);
+  rot3(cam + 9, ax, ay, az, bx, by, bz);
+  double lat = asin(bz);
+  const double lon = atan2(by, bx);
+  lat = -lat;
+  if (lon_out) *lon_out = lon;
+  if (lat_out) *lat_out = lat;
+  const double cx = double(We - 1) / 2.0, cy = double(He - 1) / 2.0;
+  const double lon_d = lon / M_PI * 180.0, lat_d = lat / M_PI * 180.0;
+  px = float(lon_d / 180.0 * cx + cx);
+  py = float(lat_d / 90.0 * cy + cy);
+}
+
+// p2e.py:9-49 (map_equi_pix_to_pers): pixel coords in the perspective image + validity mask
+__device__ __forceinline__ void p2e_grid(const double* cam, int i, int j, int He, int We, int hp, int wp, float& px,
+                                         float& py, bool& mask) {
+  const double w_len = cam[18], h_len = cam[19];
+  const double xd = np_linspace(-180.0, 180.0, We, j);
+  const double yd = np_linspace(90.0, -90.0, He, i);
+  const double xr = xd * (M_PI / 180.0), yr = yd * (M_PI / 180.0);
+  const double vx = cos(xr) * cos(yr), vy = sin(xr) * cos(yr), vz = sin(yr);
+  double ax, ay, az, bx, by, bz;
+  rot3(cam + 9, vx, vy, vz, ax, ay, az);  // inv(R2) first (p2e.py:32)
+  rot3(cam, ax, ay, az, bx, by, bz);      // then inv(R1) (p2e.py:33)
+  const bool front = bx > 0.0;
+  const double u = by / bx, v = bz / bx;
+  const bool inside = (-w_len < u) && (u < w_len) && (-h_len < v) && (v < h_len);
+  const double lon_map = inside ? (u + w_len) / 2.0 / w_len * double(wp) : 0.0;
+  const double lat_map = inside ? (-v + h_len) / 2.0 / h_len * double(hp) : 0.0;
+  px = float(lon_map);
+  py = float(lat_map);
+  mask = inside && front;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// direct variant: thread <-> output pixel, loop over a channel slice. NCHW.
+// grid = (ceil(hw_out/256), channel slices, B)
+// ---------------------------------------------------------------------------------------------------
+template <typename T, bool P2E>
+__global__ void __launch_bounds__(256)
+resample_direct_kernel(const T* __restrict__ src, T* __restrict__ dst, uint8_t* __restrict__ mask_out, int C,
+                       int Hs, int Ws, int Hd, int Wd, const double* __restrict__ cams, int cam_stride, int mode,
+                       int ch_per_slice) {
+  const int b = blockIdx.z;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= Hd * Wd) return;
+  const int r = pix / Wd, c = pix - r * Wd;
+  const double* cam = cams + (size_t)b * cam_stride * PF_CAM_DOUBLES;
+  float px, py;
+  bool live = true;
+  if constexpr (P2E) {
+    p2e_grid(cam, r, c, Hd, Wd, Hs, Ws, px, py, live);
+    if (mask_out && blockIdx.y == 0) mask_out[(size_t)b * Hd * Wd + pix] = live ? 1 : 0;
+  } else {
+    e2p_grid(cam, r, c, Hd, Wd, Hs, Ws, px, py);
+  }
+  Taps t;
+  // p2e samples everywhere `inside` holds and multiplies by mask afterwards; sample * 0 == 0 for finite data
+  make_taps(px, py, Hs, Ws, mode, live, t);
+  const int c0 = blockIdx.y * ch_per_slice;
+  const int c1 = min(C, c0 + ch_per_slice);
+  const size_t splane = (size_t)Hs * Ws, dplane = (size_t)Hd * Wd;
+  const T* sp = src + ((size_t)b * C + c0) * splane;
+  T* dp = dst + ((size_t)b * C + c0) * dplane + pix;
+  for (int ch = c0; ch < c1; ++ch) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (t.idx[k] >= 0) acc = __fadd_rn(acc, __fmul_rn(Cvt<T>::to_f(__ldg(sp + t.idx[k])), t.w[k]));
+    }
+    *dp = Cvt<T>::from_f(acc);
+    sp += splane;
+    dp += dplane;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// staged variant: CTA <-> (batch b, channel range); taps for ALL output pixels live in registers
+// (PIX_PER_THREAD each); source planes stream through a 2-deep shared-memory ring via cp.async.bulk.
+// Output stores are fully coalesced (thread <-> consecutive x), source reads hit shared memory.
+// ---------------------------------------------------------------------------------------------------
+constexpr int STG_THREADS = 256;
+
+template <typename T, bool P2E, int PPT>
+__global__ void __launch_bounds__(STG_THREADS)
+resample_staged_kernel(const T* __restrict__ src, T* __restrict__ dst, uint8_t* __restrict__ mask_out, int C,
+                       int Hs, int Ws, int Hd, int Wd, const double* __restrict__ cams, int cam_stride, int mode,
+                       int ch_per_cta, int ch_per_stage) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  const int splane = Hs * Ws, dplane = Hd * Wd;
+  const uint32_t stage_bytes = uint32_t(ch_per_stage) * splane * sizeof(T);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  T* buf0 = reinterpret_cast<T*>(smem + 128);
+  T* buf1 = reinterpret_cast<T*>(smem + 128 + ((stage_bytes + 127) & ~127u));
+
+  const int b = blockIdx.y;
+  const int c_begin = blockIdx.x * ch_per_cta;
+  const int c_end = min(C, c_begin + ch_per_cta);
+  const int n_stages = (c_end - c_begin + ch_per_stage - 1) / ch_per_stage;
+  const T* sbase = src + (size_t)b * C * splane;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int st) {
+    const int ca = c_begin + st * ch_per_stage;
+    const int nch = min(ch_per_stage, c_end - ca);
+    const uint32_t bytes = uint32_t(nch) * splane * sizeof(T);
+    mbar_expect_tx(&bars[st & 1], bytes);
+    bulk_load_1d((st & 1) ? buf1 : buf0, sbase + (size_t)ca * splane, bytes, &bars[st & 1]);
+  };
+  if (threadIdx.x == 0) {
+    issue(0);
+    if (n_stages > 1) issue(1);
+  }
+
+  // taps for this thread's output pixels (overlaps the first bulk copies)
+  const double* cam = cams + (size_t)b * cam_stride * PF_CAM_DOUBLES;
+  Taps taps[PPT];
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    const int pix = threadIdx.x + i * STG_THREADS;
+    bool live = pix < dplane;
+    float px = 0.f, py = 0.f;
+    if (live) {
+      const int r = pix / Wd, c = pix - r * Wd;
+      if constexpr (P2E) {
+        bool m;
+        p2e_grid(cam, r, c, Hd, Wd, Hs, Ws, px, py, m);
+        if (mask_out && blockIdx.x == 0) mask_out[(size_t)b * dplane + pix] = m ? 1 : 0;
+        live = m;
+      } else {
+        e2p_grid(cam, r, c, Hd, Wd, Hs, Ws, px, py);
+      }
+    }
+    make_taps(px, py, Hs, Ws, mode, live, taps[i]);
+  }
+
+  for (int st = 0; st < n_stages; ++st) {
+    mbar_wait(&bars[st & 1], (st >> 1) & 1);
+    const T* sb = (st & 1) ? buf1 : buf0;
+    const int ca = c_begin + st * ch_per_stage;
+    const int nch = min(ch_per_stage, c_end - ca);
+    T* dp = dst + ((size_t)b * C + ca) * dplane;
+    for (int ch = 0; ch < nch; ++ch) {
+      const T* sp = sb + (size_t)ch * splane;
+#pragma unroll
+      for (int i = 0; i < PPT; ++i) {
+        const int pix = threadIdx.x + i * STG_THREADS;
+        if (pix < dplane) {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (taps[i].idx[k] >= 0) acc = __fadd_rn(acc, __fmul_rn(Cvt<T>::to_f(sp[taps[i].idx[k]]), taps[i].w[k]));
+          }
+          dp[(size_t)ch * dplane + pix] = Cvt<T>::from_f(acc);
+        }
+      }
+    }
+    __syncthreads();  // everyone done with this buffer before it is refilled
+    if (threadIdx.x == 0 && st + 2 < n_stages) issue(st + 2);
+  }
+}
+
+template <typename T, bool P2E>
+static int launch_resample(const void* src, void* dst, uint8_t* mask, int B, int C, int Hs, int Ws, int Hd, int Wd,
+                           const double* cams, int cam_stride, int mode, cudaStream_t st) {
+  const int dplane = Hd * Wd;
+  const size_t plane_bytes = (size_t)Hs * Ws * sizeof(T);
+  const bool aligned = (plane_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  // staged path: plane must fit twice (double buffer) in <= ~96 KB so two CTAs share an SM, <= 8 pixels/thread
+  if (aligned && plane_bytes <= 48 * 1024 && dplane <= 8 * STG_THREADS && C >= 4) {
+    int ch_per_stage = (int)((48 * 1024) / plane_bytes);
+    if (ch_per_stage < 1) ch_per_stage = 1;
+    if (ch_per_stage > 16) ch_per_stage = 16;
+    // enough CTAs to fill 148 SMs x 2, but long enough channel runs to amortise the fp64 grid math
+    int ch_per_cta = C;
+    const int want_ctas = 148 * 2;
+    int ctas_per_b = (want_ctas + B - 1) / B;
+    if (ctas_per_b < 1) ctas_per_b = 1;
+    ch_per_cta = (C + ctas_per_b - 1) / ctas_per_b;
+    ch_per_cta = ((ch_per_cta + ch_per_stage - 1) / ch_per_stage) * ch_per_stage;
+    if (ch_per_cta > C) ch_per_cta = ((C + ch_per_stage - 1) / ch_per_stage) * ch_per_stage;
+    const int grid_x = (C + ch_per_cta - 1) / ch_per_cta;
+    const size_t stage_bytes = ((size_t)ch_per_stage * plane_bytes + 127) & ~size_t(127);
+    const size_t smem = 128 + 128 + 2 * stage_bytes;
+    dim3 grid(grid_x, B);
+    const int ppt = (dplane + STG_THREADS - 1) / STG_THREADS;
+#define PF_LAUNCH_STG(PPT)                                                                                        \
+  {                                                                                                               \
+    auto kern = resample_staged_kernel<T, P2E, PPT>;                                                              \
+    int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),       \
+                        "cudaFuncSetAttribute(resample)");                                                        \
+    if (rc) return rc;                                                                                            \
+    kern<<<grid, STG_THREADS, smem, st>>>(static_cast<const T*>(src), static_cast<T*>(dst), mask, C, Hs, Ws, Hd,  \
+                                          Wd, cams, cam_stride, mode, ch_per_cta, ch_per_stage);                  \
+  }
+    if (ppt <= 1) PF_LAUNCH_STG(1)
+    else if (ppt <= 2) PF_LAUNCH_STG(2)
+    else if (ppt <= 4) PF_LAUNCH_STG(4)
+    else PF_LAUNCH_STG(8)
+#undef PF_LAUNCH_STG
+    PF_CHECK_LAUNCH("resample_staged_kernel");
+    return PF_OK;
+  }
+  int ch_per_slice = C;
+  {
+    const long long blocks_xy = (long long)((dplane + 255) / 256) * B;
+    int slices = (int)((148LL * 8 + blocks_xy - 1) / blocks_xy);
+    if (slices < 1) slices = 1;
+    if (slices > C) slices = C;
+    ch_per_slice = (C + slices - 1) / slices;
+  }
+  dim3 grid((dplane + 255) / 256, (C + ch_per_slice - 1) / ch_per_slice, B);
+  resample_direct_kernel<T, P2E><<<grid, 256, 0, st>>>(static_cast<const T*>(src), static_cast<T*>(dst), mask, C,
+                                                       Hs, Ws, Hd, Wd, cams, cam_stride, mode, ch_per_slice);
+  PF_CHECK_LAUNCH("resample_direct_kernel");
+  return PF_OK;
+}
+
+template <bool P2E>
+static int dispatch_resample(const void* src, void* dst, uint8_t* mask, int dtype, int B, int C, int Hs, int Ws,
+                             int Hd, int Wd, const double* cams, int cam_stride, int mode, void* stream) {
+  const char* name = P2E ? "pf_p2e" : "pf_e2p";
+  PF_CHECK_ARG(src && dst && cams, "%s: null pointer", name);
+  PF_CHECK_ARG(B > 0 && C > 0 && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0, "%s: empty shape", name);
+  PF_CHECK_ARG(B <= 65535, "%s: batch %d exceeds grid limit", name, B);
+  PF_CHECK_ARG(cam_stride == 0 || cam_stride == 1, "%s: cam_stride must be 0 or 1", name);
+  // reference: choose_mode() accepts 'bilinear'/'nearest' for tensors, ValueError otherwise (utils.py:5-15)
+  PF_CHECK_ARG(mode == 0 || mode == 1, "%s: mode must be one of [bilinear, nearest]", name);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case PF_F32:
+      return launch_resample<float, P2E>(src, dst, mask, B, C, Hs, Ws, Hd, Wd, cams, cam_stride, mode, st);
+    case PF_F16:
+      return launch_resample<__half, P2E>(src, dst, mask, B, C, Hs, Ws, Hd, Wd, cams, cam_stride, mode, st);
+    case PF_BF16:
+      return launch_resample<__nv_bfloat16, P2E>(src, dst, mask, B, C, Hs, Ws, Hd, Wd, cams, cam_stride, mode, st);
+  }
+  set_error("%s: unknown dtype %d", name, dtype);
+  return PF_ERR_INVALID;
+}
+
+}  // namespace pf
+
+extern "C" int pf_e2p(const void* src, void* dst, int dtype, int B, int C, int He, int We, int h, int w,
+                      const double* cams, int cam_stride, int mode, void* stream) {
+  return pf::dispatch_resample<false>(src, dst, nullptr, dtype, B, C, He, We, h, w, cams, cam_stride, mode, stream);
+}
+
+extern "C" int pf_p2e(const void* src, void* dst, uint8_t* mask, int dtype, int B, int C, int hp, int wp, int He,
+                      int We, const double* cams, int cam_stride, int mode, void* stream) {
+  return pf::dispatch_resample<true>(src, dst, mask, dtype, B, C, hp, wp, He, We, cams, cam_stride, mode, stream);
+}

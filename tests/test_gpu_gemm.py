@@ -1,0 +1,109 @@
+"""-m gpu: tcgen05 tap-GEMM (pf_gemm_taps) against a plain PyTorch fp32 reference of the same contraction.
+
+Inputs are rounded to the 16-bit compute type first, so the only differences are fp32 accumulation order and the
+final rounding of the output: tolerance rtol 1e-3 / atol 1e-4 for fp32 outputs (north_star), and one output ulp
+(2^-8 bf16, 2^-11 fp16 relative) for 16-bit outputs.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _tol(dtype):
+    return dict(rtol=1e-3, atol=1e-4) if dtype == torch.float32 else (
+        dict(rtol=2 ** -7, atol=2e-2) if dtype == torch.bfloat16 else dict(rtol=2 ** -10, atol=2e-3))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K,bn", [(300, 320, 640, 0), (128, 64, 64, 64), (1000, 1280, 320, 128),
+                                      (257, 640, 1024, 160), (513, 1280, 256, 256), (4096, 960, 320, 0)])
+def test_linear_plain(cuda_device, dtype, M, N, K, bn):
+    from panfusion_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(dtype).to(cuda_device)
+    B = (torch.randn(N, K, generator=g) / K ** 0.5).to(dtype).to(cuda_device)
+    ref = A.float() @ B.float().T
+    out = torch.empty(M, N, dtype=torch.float32, device=cuda_device)
+    ops.gemm_taps(A, B, out, M=M, Kc=K, block_n=bn)
+    torch.testing.assert_close(out, ref, rtol=1e-3, atol=1e-4)
+    out16 = torch.empty(M, N, dtype=dtype, device=cuda_device)
+    ops.gemm_taps(A, B, out16, M=M, Kc=K, block_n=bn)
+    torch.testing.assert_close(out16.float(), ref, **_tol(dtype))
+
+
+@pytest.mark.parametrize("act", ["none", "silu", "gelu"])
+@pytest.mark.parametrize("res_dtype", [None, torch.float32, torch.bfloat16])
+def test_linear_epilogue(cuda_device, act, res_dtype):
+    from panfusion_b200 import ops
+    M, N, K = 777, 640, 320
+    g = torch.Generator(device="cpu").manual_seed(7)
+    A = torch.randn(M, K, generator=g).bfloat16().to(cuda_device)
+    B = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().to(cuda_device)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    rowbias = torch.randn(4, N, generator=g).to(cuda_device)
+    rpg = 200
+    res = None if res_dtype is None else torch.randn(M, N, generator=g).to(res_dtype).to(cuda_device)
+    ref = A.float() @ B.float().T + bias + rowbias[(torch.arange(M, device=cuda_device) // rpg)]
+    ref = {"none": lambda x: x, "silu": F.silu, "gelu": F.gelu}[act](ref)
+    if res is not None:
+        ref = ref + res.float()
+    out = torch.empty(M, N, dtype=torch.float32, device=cuda_device)
+    ops.gemm_taps(A, B, out, M=M, Kc=K, bias=bias, rowbias=rowbias, rows_per_group=rpg, residual=res,
+                  act={"none": ops.PF_ACT_NONE, "silu": ops.PF_ACT_SILU, "gelu": ops.PF_ACT_GELU}[act])
+    torch.testing.assert_close(out, ref, rtol=1e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("N2,bn", [(2560, 160), (1280, 128), (5120, 0)])
+def test_geglu(cuda_device, N2, bn):
+    """GEGLU (models/modules/transformer.py:8-16): proj -> chunk(2) -> x * gelu(gate)."""
+    from panfusion_b200 import ops
+    from panfusion_b200.packing import pack_geglu
+    M, K = 500, 320
+    g = torch.Generator(device="cpu").manual_seed(3)
+    A = torch.randn(M, K, generator=g).bfloat16().to(cuda_device)
+    W = (torch.randn(N2, K, generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N2, generator=g)
+    y = A.float() @ W.float().T.to(cuda_device) + b.to(cuda_device)
+    x, gate = y.chunk(2, dim=-1)
+    ref = x * F.gelu(gate)
+    block_n = bn or ops.pick_block_n(N2, ops.PF_ACT_GEGLU)
+    Wp, bp = pack_geglu(W, b, block_n)
+    out = torch.empty(M, N2 // 2, dtype=torch.float32, device=cuda_device)
+    ops.gemm_taps(A, Wp.to(cuda_device), out, M=M, Kc=K, bias=bp.to(cuda_device), act=ops.PF_ACT_GEGLU,
+                  block_n=block_n)
+    torch.testing.assert_close(out, ref, rtol=1e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("n,H,W,Cin,Cout", [(2, 8, 12, 64, 128), (3, 16, 16, 320, 320), (1, 8, 20, 128, 64),
+                                            (2, 64, 64, 64, 160)])
+def test_conv3x3_taps(cuda_device, n, H, W, Cin, Cout):
+    """3x3 / pad 1 convolution as 9 taps over the zero-haloed channels-last image."""
+    from panfusion_b200 import ops
+    from panfusion_b200.packing import pack_conv3x3
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = torch.randn(n, Cin, H, W, generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).bfloat16()
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x.float(), w.float(), b, padding=1).to(cuda_device)
+    Hp, Wp = H + 2, W + 2
+    xp = torch.zeros(n, Hp, Wp, Cin, dtype=torch.bfloat16)
+    xp[:, 1:-1, 1:-1] = x.permute(0, 2, 3, 1)
+    A = xp.reshape(n * Hp * Wp, Cin).to(cuda_device)
+    Bw = pack_conv3x3(w).to(cuda_device)
+    taps = [(dy - 1) * Wp + (dx - 1) for dy in range(3) for dx in range(3)]
+    out = torch.empty(n * H * W, Cout, dtype=torch.float32, device=cuda_device)
+    ops.gemm_taps(A, Bw, out, M=n * Hp * Wp, Kc=Cin, taps=taps, bias=b.to(cuda_device),
+                  image_map=(Hp, Wp, 1, 1, H, W))
+    got = out.reshape(n, H, W, Cout).permute(0, 3, 1, 2)
+    torch.testing.assert_close(got, ref, rtol=1e-3, atol=2e-4)
+
+
+def test_bad_args_raise(cuda_device):
+    from panfusion_b200 import ops
+    A = torch.zeros(128, 72, dtype=torch.bfloat16, device=cuda_device)
+    B = torch.zeros(64, 72, dtype=torch.bfloat16, device=cuda_device)
+    out = torch.zeros(128, 64, dtype=torch.float32, device=cuda_device)
+    with pytest.raises(ValueError):
+        ops.gemm_taps(A, B, out, M=128, Kc=72)  # Kc not a multiple of 64
