@@ -104,6 +104,33 @@ int pf_gemm_taps(const pf_gemm_args* args, void* stream);
 /* block_n the auto-tuner would pick for this N (used by the host-side weight packer for GEGLU) */
 int pf_gemm_pick_block_n(int N, int act);
 
+/* ------------------------------------------------------------------------------------------------
+ * Flash attention forward (tcgen05): out = softmax(q k^T * scale + bias) v, fp32 softmax / accumulation.
+ * Replaces xformers.ops.memory_efficient_attention at models/modules/transformer.py:71 (EPPA: head_dim 32,
+ * additive fp32 bias shared by every head — transformer.py:68 materialises it per head, this never does) and the
+ * bmm-softmax-bmm of the diffusers attention blocks walked at models/pano/MVGenModel.py:104,116,185,190,227,241
+ * (head_dim 64, self and 77-token text cross attention).
+ * q/k/v: 16-bit, element (b, l, h, d) at ptr[b*bstride + l*ld + h*head_dim + d] (so fused QKV buffers work
+ * in place); out: [B, Lq, out_ld] same dtype. bias: fp32 [*, Lq, bias_ld], batch b reads bias + b*bias_bstride
+ * (0 = one table for all batches), or NULL. Any Lq / Lk >= 1 (ragged tiles are masked).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct pf_fmha_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  int32_t dtype;
+  int32_t B, H, Lq, Lk, head_dim;
+  int32_t q_ld, k_ld, v_ld, out_ld;
+  int64_t q_bstride, k_bstride, v_bstride;
+  float scale;
+  const float* bias;
+  int64_t bias_bstride;
+  int32_t bias_ld;
+} pf_fmha_args;
+
+int pf_fmha_fwd(const pf_fmha_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

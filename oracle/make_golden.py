@@ -1,0 +1,107 @@
+"""Mint tests/golden/*.npz by EXECUTING THE REFERENCE'S OWN FILES (oracle/ref_loader.py) on seeded inputs, and
+check the oracle restatement against them. Runs only where /root/reference is mounted (the build container).
+
+    python -m oracle.make_golden [--full]     # --full adds the SD-2-size C1 step (minutes on 8 cores)
+
+Each fixture stores the seeded inputs' identifying parameters and the reference outputs; tests regenerate the
+inputs from the seeds (same torch build on both boxes) and compare.
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import eppa as oe, geometry as og, mvgen as om, ref_loader, synth, unet as ounet
+
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+def _cams3():
+    return dict(FoV=torch.tensor([90.0, 75.0, 100.0]), theta=torch.tensor([0.0, 45.0, 200.0]),
+                phi=torch.tensor([0.0, 30.0, -60.0]))
+
+
+def _report(name, ref, mine):
+    err = max((a - b).abs().max().item() for a, b in zip(ref, mine))
+    print(f"  {name}: max |oracle - reference| = {err:.3e}")
+    return err
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true")
+    args = ap.parse_args()
+    ref = ref_loader.load()
+    OUT.mkdir(parents=True, exist_ok=True)
+    torch.set_grad_enabled(False)
+    worst = 0.0
+
+    # 1. resampling (e2p.py:54-76, p2e.py:52-77)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 5, 32, 64, generator=g)
+    y = torch.randn(3, 5, 16, 24, generator=g)
+    c = _cams3()
+    out = {}
+    for mode in ("bilinear", "nearest"):
+        r = ref.e2p(x, c["FoV"], c["theta"], c["phi"], (16, 24), mode=mode)
+        out[f"e2p_{mode}"] = r.numpy()
+        worst = max(worst, _report(f"e2p {mode}", [r], [og.e2p(x, c["FoV"], c["theta"], c["phi"], (16, 24), mode=mode)]))
+        r, rm = ref.p2e(y, c["FoV"], c["theta"], c["phi"], (32, 64), mode=mode)
+        out[f"p2e_{mode}"], out[f"p2e_{mode}_mask"] = r.numpy(), rm.numpy()
+        mo, mm = og.p2e(y, c["FoV"], c["theta"], c["phi"], (32, 64), mode=mode)
+        worst = max(worst, _report(f"p2e {mode}", [r, rm.float()], [mo, mm.float()]))
+    r = ref.e2p(x, 90, 10, 5, (16, 16))
+    out["e2p_scalar"] = r.numpy()
+    np.savez_compressed(OUT / "resample.npz", **out)
+
+    # 2. EPPA geometry (models/pano/utils.py:10-106)
+    pm, em = ref.get_masks(8, 8, 8, 16, c, "cpu")
+    pc, ec = ref.get_coords(8, 8, 8, 16, c, "cpu")
+    worst = max(worst, _report("get_masks", [pm, em], oe.get_masks(8, 8, 8, 16, c)))
+    worst = max(worst, _report("get_coords", [pc, ec], oe.get_coords(8, 8, 8, 16, c)))
+    np.savez_compressed(OUT / "eppa_geometry.npz", pers_masks=pm.numpy(), equi_masks=em.numpy(),
+                        pers_coords=pc.numpy(), equi_coords=ec.numpy())
+
+    # 3. WarpAttn (models/pano/modules.py:8-59), dim 320, 2 batches x 2 views
+    torch.manual_seed(7)
+    wr = ref.WarpAttn(320).eval()
+    holder = torch.nn.Module()
+    holder.cp_blocks = wr
+    synth.randomize_zero_init(holder, 11)
+    wm = oe.WarpAttn(320).eval()
+    wm.load_state_dict(wr.state_dict())
+    g = torch.Generator().manual_seed(8)
+    px, ex = torch.randn(4, 320, 8, 8, generator=g), torch.randn(2, 320, 8, 16, generator=g)
+    c4 = dict(FoV=torch.full((4,), 90.0), theta=torch.tensor([0.0, 180.0, 0.0, 180.0]), phi=torch.zeros(4))
+    rp, re = wr(px, ex, c4)
+    worst = max(worst, _report("WarpAttn", [rp, re], wm(px, ex, c4)))
+    np.savez_compressed(OUT / "warpattn_320.npz", pers_out=rp.numpy(), equi_out=re.numpy())
+
+    # 4. MultiViewBaseModel (models/pano/MVGenModel.py:38-297) with narrow UNets: m=2, pers 16x16, pano 16x32
+    def mv(config, pano_hw, pers_hw, tag):
+        model_r = synth.build_model(ref.MultiViewBaseModel, config, seed=0)
+        model_o = synth.build_model(om.MultiViewBaseModel, config, seed=0)
+        model_o.load_state_dict(model_r.state_dict())
+        inp = synth.step_inputs(2, pano_hw, pers_hw, config["cross_attention_dim"], seed=0)
+        t0 = time.time()
+        rs, rp_ = model_r(**inp)
+        t1 = time.time()
+        os_, op_ = model_o(**inp)
+        print(f"  [{tag}] reference {t1 - t0:.1f}s oracle {time.time() - t1:.1f}s")
+        np.savez_compressed(OUT / f"mvgen_{tag}.npz", sample=rs.numpy(), pano_sample=rp_.numpy())
+        return _report(f"MultiViewBaseModel {tag}", [rs, rp_], [os_, op_])
+
+    worst = max(worst, mv(ounet.TINY_CONFIG, (16, 32), (16, 16), "tiny"))
+    if args.full:
+        worst = max(worst, mv(ounet.SD2_CONFIG, (64, 128), (64, 64), "c1"))
+    print(f"worst oracle-vs-reference deviation: {worst:.3e}")
+    return 0 if worst < 1e-4 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

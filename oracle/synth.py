@@ -1,0 +1,43 @@
+"""Seeded synthetic inputs / weights shared by the golden generator, the tests and bench.py.
+Test infrastructure only."""
+from __future__ import annotations
+
+import torch
+
+from . import sampler, unet as ounet
+
+
+def randomize_zero_init(model: torch.nn.Module, seed: int = 1234, std: float = 0.02) -> None:
+    """EPPA output projections are zero-initialised (transformer.py:29-30,54-55), which makes a fresh WarpAttn the
+    identity and hides bugs: redraw every all-zero parameter of the cp_blocks from N(0, std^2), deterministically."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in sorted(model.named_parameters()):
+            if "cp_blocks" in name and p.abs().sum() == 0:
+                p.copy_(torch.randn(p.shape, generator=g) * std)
+
+
+def step_inputs(m: int, pano_hw, pers_hw, ctx_dim: int, seed: int = 0, batch: int = 1, t: int = 981):
+    """Inputs of ONE MultiViewBaseModel.forward call (no CFG duplication): latents via init_noise's shared field."""
+    g = torch.Generator().manual_seed(seed)
+    cams = sampler.horizon_cameras(m, batch=batch)
+    pano = torch.randn(batch, 1, 4, *pano_hw, generator=g)
+    lat = sampler.init_noise(pano, pers_hw[0], pers_hw[1], cams)
+    ts = torch.full((batch, m), t, dtype=torch.long)
+    prompt = torch.randn(batch, 1, 77, ctx_dim, generator=g).repeat(1, m, 1, 1)  # copy_pano_prompt (PanFusion.py:17)
+    pano_prompt = prompt[:, :1].clone()
+    return dict(latents=lat, pano_latent=pano, timestep=ts, prompt_embd=prompt, pano_prompt_embd=pano_prompt,
+                cameras=cams)
+
+
+def build_model(model_cls, config=None, seed: int = 0):
+    """Two independently seeded UNets + the EPPA blocks with their zero-init tensors redrawn."""
+    config = config or ounet.SD2_CONFIG
+    st = torch.random.get_rng_state()
+    torch.manual_seed(seed + 100)
+    unet = ounet.build_unet(config, seed=seed + 1)
+    pano_unet = ounet.build_unet(config, seed=seed + 2)
+    model = model_cls(unet, pano_unet).eval()
+    torch.random.set_rng_state(st)
+    randomize_zero_init(model, seed + 3)
+    return model

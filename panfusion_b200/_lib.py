@@ -38,6 +38,17 @@ class GemmArgs(C.Structure):
     ]
 
 
+class FmhaArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+        ("dtype", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32),
+        ("head_dim", C.c_int32),
+        ("q_ld", C.c_int32), ("k_ld", C.c_int32), ("v_ld", C.c_int32), ("out_ld", C.c_int32),
+        ("q_bstride", C.c_int64), ("k_bstride", C.c_int64), ("v_bstride", C.c_int64),
+        ("scale", C.c_float), ("bias", C.c_void_p), ("bias_bstride", C.c_int64), ("bias_ld", C.c_int32),
+    ]
+
+
 _lib = None
 
 
@@ -62,6 +73,7 @@ EXPORTS = [
     "pf_last_error", "pf_version", "pf_check_device",
     "pf_e2p", "pf_p2e",
     "pf_gemm_taps", "pf_gemm_pick_block_n",
+    "pf_fmha_fwd",
 ]
 
 

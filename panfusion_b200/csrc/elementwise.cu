@@ -1,0 +1,244 @@
+// Small bandwidth-bound kernels at the edges of the UNet walk (models/pano/MVGenModel.py:52-60,85-91,279-295) and of
+// the sampling loop (models/pano/PanFusion.py:146-162, PanoGenerator.py:253-269).
+#include "pf_common.cuh"
+
+namespace pf {
+
+// ------------------------------------------------------------------------------------------------
+// conv_in: NCHW fp32 latent [N,Cin<=8,H,W] -> channels-last tokens [N*H*W, Cout] (3x3, pad 1; `circ` wraps
+// columns == pad_pano(1) -> conv -> unpad_pano(1), MVGenModel.py:87-91). Weights fp32 [Cout, Cin, 3, 3].
+// thread <-> (pixel, 8 output channels)
+// ------------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+               uint16_t* __restrict__ out, int N, int Cin, int H, int W, int Cout, int circ) {
+  const int vecs = Cout / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * H * W * vecs) return;
+  const int v = int(idx % vecs);
+  const long long pix = idx / vecs;
+  const int xx = int(pix % W), yy = int((pix / W) % H), n = int(pix / ((long long)W * H));
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = bias ? __ldg(bias + v * 8 + e) : 0.f;
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float* xp = x + ((size_t)n * Cin + ci) * H * W;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int sy = yy + dy - 1;
+      if (sy < 0 || sy >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        int sx = xx + dx - 1;
+        if (circ) {
+          sx = sx < 0 ? sx + W : (sx >= W ? sx - W : sx);
+        } else if (sx < 0 || sx >= W) {
+          continue;
+        }
+        const float val = __ldg(xp + sy * W + sx);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(val, __ldg(w + (((size_t)(v * 8 + e) * Cin + ci) * 3 + dy) * 3 + dx), acc[e]);
+      }
+    }
+  }
+  *reinterpret_cast<uint4*>(out + (size_t)pix * Cout + v * 8) =
+      make_uint4(pack2<BF16>(acc[0], acc[1]), pack2<BF16>(acc[2], acc[3]), pack2<BF16>(acc[4], acc[5]),
+                 pack2<BF16>(acc[6], acc[7]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_out: tokens [N,H,W,C] -> GroupNorm -> SiLU -> conv 3x3 (C -> Cout<=4) -> NCHW fp32 (MVGenModel.py:279-295).
+// one warp per output pixel; weights fp32 [Cout, C, 3, 3] re-laid in smem as [tap][Cout][C].
+// ------------------------------------------------------------------------------------------------
+constexpr int CONV_OUT_PIX_PER_BLOCK = 64;
+
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+conv_out_kernel(const uint16_t* __restrict__ x, int ld, const float* __restrict__ mean_rstd,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int groups,
+                const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out, int N, int H,
+                int W, int C, int Cout, int circ) {
+  extern __shared__ float s_w[];  // [9][Cout][C] + scale[C] + shift[C] per image handled by this block
+  float* s_scale = s_w + 9 * Cout * C;
+  float* s_shift = s_scale + C;
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < 9 * Cout * C; i += blockDim.x) {
+    const int c = i % C, co = (i / C) % Cout, tap = i / (C * Cout);
+    s_w[i] = w[((size_t)co * C + c) * 9 + tap];
+  }
+  const int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mean = mean_rstd[((size_t)n * groups + g) * 2], rstd = mean_rstd[((size_t)n * groups + g) * 2 + 1];
+    const float sc = rstd * gamma[c];
+    s_scale[c] = sc;
+    s_shift[c] = beta[c] - mean * sc;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int pi = warp; pi < CONV_OUT_PIX_PER_BLOCK; pi += (blockDim.x >> 5)) {
+  const int pix = blockIdx.x * CONV_OUT_PIX_PER_BLOCK + pi;
+  if (pix >= H * W) break;
+  const int yy = pix / W, xx = pix % W;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int dy = 0; dy < 3; ++dy) {
+    const int sy = yy + dy - 1;
+    if (sy < 0 || sy >= H) continue;
+    for (int dx = 0; dx < 3; ++dx) {
+      int sx = xx + dx - 1;
+      if (circ) sx = sx < 0 ? sx + W : (sx >= W ? sx - W : sx);
+      else if (sx < 0 || sx >= W) continue;
+      const uint16_t* xr = x + ((size_t)n * H * W + (size_t)sy * W + sx) * ld;
+      const float* wt = s_w + (dy * 3 + dx) * Cout * C;
+      for (int c = lane * 2; c < C; c += 64) {
+        const float2 f = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(xr + c));
+        const float a0 = silu_f(f.x * s_scale[c] + s_shift[c]);
+        const float a1 = silu_f(f.y * s_scale[c + 1] + s_shift[c + 1]);
+        for (int co = 0; co < Cout; ++co) acc[co] += a0 * wt[co * C + c] + a1 * wt[co * C + c + 1];
+      }
+    }
+  }
+  for (int co = 0; co < Cout; ++co) {
+    const float v = warp_sum(acc[co]);
+    if (lane == 0) out[(((size_t)n * Cout + co) * H + yy) * W + xx] = v + (bias ? bias[co] : 0.f);
+  }
+  }
+}
+
+// strided 2-D copy of 16-bit rows (skip concatenation: torch.cat at MVGenModel.py:223,231,246,254)
+__global__ void __launch_bounds__(256)
+copy2d_kernel(const uint16_t* __restrict__ src, int src_ld, uint16_t* __restrict__ dst, int dst_ld, long long rows,
+              int cols) {
+  const int vecs = cols / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * vecs) return;
+  const long long r = idx / vecs;
+  const int v = int(idx % vecs);
+  *reinterpret_cast<uint4*>(dst + r * dst_ld + v * 8) = __ldg(reinterpret_cast<const uint4*>(src + r * src_ld + v * 8));
+}
+
+// diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos(t f_i) | sin(t f_i)], f_i = 10000^(-i/half)
+template <bool BF16>
+__global__ void timestep_embed_kernel(const float* __restrict__ t, uint16_t* __restrict__ out, int n, int dim) {
+  const int half = dim / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * half) return;
+  const int r = idx / half, i = idx % half;
+  const float freq = expf(-logf(10000.0f) * float(i) / float(half));
+  const float ang = t[r] * freq;
+  const float c = cosf(ang), s = sinf(ang);
+  if constexpr (BF16) {
+    reinterpret_cast<__nv_bfloat16*>(out)[(size_t)r * dim + i] = __float2bfloat16_rn(c);
+    reinterpret_cast<__nv_bfloat16*>(out)[(size_t)r * dim + half + i] = __float2bfloat16_rn(s);
+  } else {
+    reinterpret_cast<__half*>(out)[(size_t)r * dim + i] = __float2half_rn(c);
+    reinterpret_cast<__half*>(out)[(size_t)r * dim + half + i] = __float2half_rn(s);
+  }
+}
+
+// CFG combine + DDIM update (+ optional column roll of the result): PanoGenerator.py:253-262, DDIMScheduler.step,
+// PanoGenerator.py:264-269. eps holds [uncond | text] halves of `count` elements each; x, out are [rows, W] fp32.
+__global__ void __launch_bounds__(256)
+cfg_ddim_kernel(const float* __restrict__ x, const float* __restrict__ eps, float* __restrict__ out, long long count,
+                int W, int roll, float guidance, float c_x, float c_eps) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  const float eu = eps[idx], ec = eps[count + idx];
+  const float e = eu + guidance * (ec - eu);
+  const float v = c_x * x[idx] + c_eps * e;
+  long long o = idx;
+  if (roll) {
+    const int col = int(idx % W);
+    int nc = (col + roll) % W;
+    if (nc < 0) nc += W;
+    o = idx - col + nc;
+  }
+  out[o] = v;
+}
+
+}  // namespace pf
+
+extern "C" int pf_conv_in(const float* x, const float* w, const float* bias, void* out, int dtype, int N, int Cin,
+                          int H, int W, int Cout, int circ, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(x && w && out, "pf_conv_in: null pointer");
+  PF_CHECK_ARG(dtype == PF_BF16 || dtype == PF_F16, "pf_conv_in: 16-bit output dtype required");
+  PF_CHECK_ARG(N > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0 && Cout % 8 == 0, "pf_conv_in: bad shape");
+  const long long total = (long long)N * H * W * (Cout / 8);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == PF_BF16)
+    conv_in_kernel<true><<<blocks, 256, 0, st>>>(x, w, bias, static_cast<uint16_t*>(out), N, Cin, H, W, Cout, circ);
+  else
+    conv_in_kernel<false><<<blocks, 256, 0, st>>>(x, w, bias, static_cast<uint16_t*>(out), N, Cin, H, W, Cout, circ);
+  PF_CHECK_LAUNCH("conv_in_kernel");
+  return PF_OK;
+}
+
+extern "C" int pf_conv_out(const void* x, int ld, int dtype, const float* mean_rstd, const float* gamma,
+                           const float* beta, int groups, const float* w, const float* bias, float* out, int N, int H,
+                           int W, int C, int Cout, int circ, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(x && mean_rstd && gamma && beta && w && out, "pf_conv_out: null pointer");
+  PF_CHECK_ARG(dtype == PF_BF16 || dtype == PF_F16, "pf_conv_out: 16-bit input dtype required");
+  PF_CHECK_ARG(N > 0 && N <= 65535 && H > 0 && W > 0 && C % 2 == 0 && C % groups == 0 && Cout >= 1 && Cout <= 4 &&
+                   ld >= C && ld % 2 == 0,
+               "pf_conv_out: bad shape");
+  const size_t smem = ((size_t)9 * Cout * C + 2 * C) * sizeof(float);
+  PF_CHECK_ARG(smem <= 200 * 1024, "pf_conv_out: C=%d too large", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((H * W + CONV_OUT_PIX_PER_BLOCK - 1) / CONV_OUT_PIX_PER_BLOCK, N);
+  int rc;
+  if (dtype == PF_BF16) {
+    auto k = conv_out_kernel<true>;
+    if ((rc = check_cuda(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv_out attr"))) return rc;
+    k<<<grid, 256, smem, st>>>(static_cast<const uint16_t*>(x), ld, mean_rstd, gamma, beta, groups, w, bias, out, N, H, W, C, Cout, circ);
+  } else {
+    auto k = conv_out_kernel<false>;
+    if ((rc = check_cuda(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv_out attr"))) return rc;
+    k<<<grid, 256, smem, st>>>(static_cast<const uint16_t*>(x), ld, mean_rstd, gamma, beta, groups, w, bias, out, N, H, W, C, Cout, circ);
+  }
+  PF_CHECK_LAUNCH("conv_out_kernel");
+  return PF_OK;
+}
+
+extern "C" int pf_copy2d(const void* src, int src_ld, void* dst, int dst_ld, long long rows, int cols, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(src && dst, "pf_copy2d: null pointer");
+  PF_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && src_ld % 8 == 0 && dst_ld % 8 == 0 && src_ld >= cols && dst_ld >= cols,
+               "pf_copy2d: bad shape rows=%lld cols=%d", rows, cols);
+  PF_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "pf_copy2d: pointers must be 16-byte aligned");
+  const long long total = rows * (cols / 8);
+  copy2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(src), src_ld, static_cast<uint16_t*>(dst), dst_ld, rows, cols);
+  PF_CHECK_LAUNCH("copy2d_kernel");
+  return PF_OK;
+}
+
+extern "C" int pf_timestep_embed(const float* t, void* out, int dtype, int n, int dim, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(t && out && n > 0 && dim > 0 && dim % 2 == 0, "pf_timestep_embed: bad arguments");
+  PF_CHECK_ARG(dtype == PF_BF16 || dtype == PF_F16, "pf_timestep_embed: 16-bit output dtype required");
+  const int total = n * dim / 2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == PF_BF16) timestep_embed_kernel<true><<<(total + 127) / 128, 128, 0, st>>>(t, static_cast<uint16_t*>(out), n, dim);
+  else timestep_embed_kernel<false><<<(total + 127) / 128, 128, 0, st>>>(t, static_cast<uint16_t*>(out), n, dim);
+  PF_CHECK_LAUNCH("timestep_embed_kernel");
+  return PF_OK;
+}
+
+extern "C" int pf_cfg_ddim_step(const float* x, const float* eps, float* out, long long count, int W, int roll,
+                                float guidance, float alpha_t, float alpha_prev, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(x && eps && out && count > 0 && W > 0 && count % W == 0, "pf_cfg_ddim_step: bad arguments");
+  PF_CHECK_ARG(alpha_t > 0.f && alpha_t <= 1.f && alpha_prev > 0.f && alpha_prev <= 1.f, "pf_cfg_ddim_step: bad alphas");
+  // x_prev = sqrt(a_prev) * (x - sqrt(1-a_t) e) / sqrt(a_t) + sqrt(1-a_prev) e
+  const double sa = sqrt((double)alpha_prev / (double)alpha_t);
+  const float c_x = (float)sa;
+  const float c_eps = (float)(sqrt(1.0 - (double)alpha_prev) - sa * sqrt(1.0 - (double)alpha_t));
+  cfg_ddim_kernel<<<(unsigned)((count + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, eps, out, count, W, roll, guidance, c_x, c_eps);
+  PF_CHECK_LAUNCH("cfg_ddim_kernel");
+  return PF_OK;
+}

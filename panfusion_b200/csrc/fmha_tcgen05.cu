@@ -1,0 +1,337 @@
+// Flash-attention forward on tcgen05: S = Q K^T and O += P V on the 5th-gen tensor cores (accumulators in
+// TMEM), TMA-fed K/V ring, online softmax by one warpgroup (thread <-> query row), optional additive fp32 bias
+// shared by all heads (the EPPA correspondence bias).
+//
+// Replaces: xformers.ops.memory_efficient_attention(q, k, v, attn_bias) at models/modules/transformer.py:71
+// (EPPA, head dim 32, dense bias repeated per head at :68 — here never repeated) and the diffusers AttnProcessor
+// bmm-softmax-bmm inside Transformer2DModel (MVGenModel.py:104,116,185,190,227,241; head dim 64, self and text
+// cross attention).
+//
+// Tile: 128 queries x 64 keys. S is double-buffered in TMEM so Q K^T of tile j+1 runs under the softmax of tile j;
+// P goes registers -> swizzled smem (K-major A operand), P V lands in a TMEM scratch tile that the softmax
+// threads fold into their fp32 register accumulator with the online-softmax rescale.
+// 192 threads: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2..5 softmax / epilogue.
+#include "pf_common.cuh"
+
+namespace pf {
+
+constexpr int FA_BLOCK_M = 128;
+constexpr int FA_BLOCK_N = 64;
+constexpr int FA_STAGES = 4;
+constexpr int FA_THREADS = 192;
+
+struct FmhaParams {
+  int B, H, Lq, Lk;
+  float scale_log2;  // softmax scale * log2(e)
+  void* out;         // [B, Lq, out_ld] 16-bit, head h at columns [h*D, (h+1)*D)
+  int out_ld;
+  const float* bias;  // [bias_batches, Lq, bias_ld] or null
+  long long bias_bstride;
+  int bias_ld;
+};
+
+template <int D>
+__host__ __device__ constexpr int fmha_smem_bytes() {
+  return FA_BLOCK_M * D * 2 + FA_STAGES * 2 * FA_BLOCK_N * D * 2 + FA_BLOCK_M * FA_BLOCK_N * 2 + 1024 + 256;
+}
+
+template <int D, bool BF16, bool HAS_BIAS>
+__global__ void __launch_bounds__(FA_THREADS, 2)
+fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
+  static_assert(D == 32 || D == 64, "head dim 32 (EPPA) or 64 (SD-2 UNet)");
+  constexpr int Q_BYTES = FA_BLOCK_M * D * 2;
+  constexpr int KV_BYTES = FA_BLOCK_N * D * 2;  // one of K or V
+  constexpr int P_BYTES = FA_BLOCK_M * FA_BLOCK_N * 2;
+  constexpr uint32_t SW_LAYOUT = (D == 64) ? 2u : 4u;     // 128B / 64B swizzle
+  constexpr uint32_t SW_ATOM_BYTES = (D == 64) ? 1024u : 512u;  // 8 rows of D*2 bytes
+  constexpr int TMEM_COLS = 256;
+  constexpr uint32_t TM_S0 = 0, TM_S1 = 64, TM_O = 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + Q_BYTES;                       // stage s: K at s*2*KV_BYTES, V right after
+  uint8_t* sP = sKV + FA_STAGES * 2 * KV_BYTES;      // [128][64] 16-bit, SW128 K-major
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + FA_STAGES;
+  uint64_t* s_full = kv_empty + FA_STAGES;  // [2]
+  uint64_t* p_full = s_full + 2;
+  uint64_t* o_full = p_full + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x % p.H;  // heads fastest: CTAs sharing a bias tile run together (L2 reuse)
+  const int qt = blockIdx.x / p.H;
+  const int b = blockIdx.y;
+  const int q0 = qt * FA_BLOCK_M;
+  const int n_tiles = (p.Lk + FA_BLOCK_N - 1) / FA_BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < FA_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Q_BYTES);
+      tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % FA_STAGES;
+        mbar_wait(&kv_empty[s], ((j / FA_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], 2 * KV_BYTES);
+        uint8_t* dst = sKV + s * 2 * KV_BYTES;
+        tma_load_4d(dst, &tmK, &kv_full[s], 0, h, j * FA_BLOCK_N, b);
+        tma_load_4d(dst + KV_BYTES, &tmV, &kv_full[s], 0, h, j * FA_BLOCK_N, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(BF16 ? 1 : 0, FA_BLOCK_M, FA_BLOCK_N, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_f16(BF16 ? 1 : 0, FA_BLOCK_M, D, 0, 1);  // V is MN-major
+      const uint64_t qdesc = make_smem_desc(smem_u32(sQ), 16, SW_ATOM_BYTES, SW_LAYOUT);
+      const uint64_t pdesc = make_smem_desc(smem_u32(sP), 16, 1024, 2);
+      auto issue_qk = [&](int j) {
+        const int s = j % FA_STAGES;
+        mbar_wait(&kv_full[s], (j / FA_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t kdesc = make_smem_desc(smem_u32(sKV + s * 2 * KV_BYTES), 16, SW_ATOM_BYTES, SW_LAYOUT);
+        const uint32_t td = tmem_base + ((j & 1) ? TM_S1 : TM_S0);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) umma_f16(td, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_qk(j + 1);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const int s = j % FA_STAGES;
+        // V tile [64 keys][D]: MN-major B operand; 8-key groups are SW_ATOM_BYTES apart (SBO); one atom along N
+        const uint64_t vdesc =
+            make_smem_desc(smem_u32(sKV + s * 2 * KV_BYTES + KV_BYTES), SW_ATOM_BYTES, SW_ATOM_BYTES, SW_LAYOUT);
+#pragma unroll
+        for (int k = 0; k < FA_BLOCK_N / 16; ++k) {
+          // P: +32 B per 16 keys inside the 128 B swizzle row; V: +16 key rows = 2 swizzle atoms
+          umma_f16(tmem_base + TM_O, pdesc + 2 * k, vdesc + uint64_t((2 * SW_ATOM_BYTES * k) >> 4), idesc_pv, k != 0);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int q = q0 + row;
+    const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+    float o_acc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) o_acc[d] = 0.f;
+    const float* bias_row = nullptr;
+    if constexpr (HAS_BIAS) {
+      const int qq = q < p.Lq ? q : p.Lq - 1;
+      bias_row = p.bias + (long long)b * p.bias_bstride + (long long)qq * p.bias_ld;
+    }
+    constexpr float LOG2E = 1.4426950408889634f;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      float sv[FA_BLOCK_N];
+      {
+        uint32_t raw[32];
+        const uint32_t ts = lane_addr + ((j & 1) ? TM_S1 : TM_S0);
+        tmem_ld32(ts, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) sv[e] = __uint_as_float(raw[e]) * p.scale_log2;
+        tmem_ld32(ts + 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) sv[32 + e] = __uint_as_float(raw[e]) * p.scale_log2;
+      }
+      const int k0 = j * FA_BLOCK_N;
+      if constexpr (HAS_BIAS) {
+        if (k0 + FA_BLOCK_N <= p.Lk) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias_row + k0);
+#pragma unroll
+          for (int e = 0; e < FA_BLOCK_N / 4; ++e) {
+            const float4 t = __ldg(b4 + e);
+            sv[4 * e + 0] = fmaf(t.x, LOG2E, sv[4 * e + 0]);
+            sv[4 * e + 1] = fmaf(t.y, LOG2E, sv[4 * e + 1]);
+            sv[4 * e + 2] = fmaf(t.z, LOG2E, sv[4 * e + 2]);
+            sv[4 * e + 3] = fmaf(t.w, LOG2E, sv[4 * e + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < FA_BLOCK_N; ++e)
+            if (k0 + e < p.Lk) sv[e] = fmaf(__ldg(bias_row + k0 + e), LOG2E, sv[e]);
+        }
+      }
+      if (k0 + FA_BLOCK_N > p.Lk) {
+#pragma unroll
+        for (int e = 0; e < FA_BLOCK_N; ++e)
+          if (k0 + e >= p.Lk) sv[e] = -INFINITY;
+      }
+      float mx = m_run;
+#pragma unroll
+      for (int e = 0; e < FA_BLOCK_N; ++e) mx = fmaxf(mx, sv[e]);
+      const float alpha = exp2f(m_run - mx);
+      m_run = mx;
+      float psum = 0.f;
+      uint32_t pk[FA_BLOCK_N / 2];
+#pragma unroll
+      for (int e = 0; e < FA_BLOCK_N; e += 2) {
+        const float p0 = exp2f(sv[e] - mx), p1 = exp2f(sv[e + 1] - mx);
+        // the row sum uses the rounded probabilities that the P V MMA consumes
+        pk[e >> 1] = pack2<BF16>(p0, p1);
+        const float2 r = unpack2<BF16>(pk[e >> 1]);
+        psum += r.x + r.y;
+      }
+      l_run = l_run * alpha + psum;
+
+      if (j > 0) {
+        // fold P V of tile j-1 (this also proves the tensor core is done reading sP)
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+        uint32_t raw[32];
+#pragma unroll
+        for (int c = 0; c < D; c += 32) {
+          tmem_ld32(lane_addr + TM_O + c, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o_acc[c + e] = o_acc[c + e] * alpha_prev + __uint_as_float(raw[e]);
+        }
+      }
+      alpha_prev = alpha;
+      // P row -> swizzled smem: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
+      {
+        uint8_t* prow = sP + row * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 v = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = v;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // last tile's P V
+    mbar_wait(o_full, (n_tiles - 1) & 1);
+    tc_fence_after();
+    {
+      uint32_t raw[32];
+#pragma unroll
+      for (int c = 0; c < D; c += 32) {
+        tmem_ld32(lane_addr + TM_O + c, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o_acc[c + e] = o_acc[c + e] * alpha_prev + __uint_as_float(raw[e]);
+      }
+    }
+    if (q < p.Lq) {
+      const float inv = 1.0f / l_run;
+      uint16_t* orow = static_cast<uint16_t*>(p.out) + ((long long)b * p.Lq + q) * p.out_ld + h * D;
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        uint4 v = make_uint4(pack2<BF16>(o_acc[c] * inv, o_acc[c + 1] * inv),
+                             pack2<BF16>(o_acc[c + 2] * inv, o_acc[c + 3] * inv),
+                             pack2<BF16>(o_acc[c + 4] * inv, o_acc[c + 5] * inv),
+                             pack2<BF16>(o_acc[c + 6] * inv, o_acc[c + 7] * inv));
+        *reinterpret_cast<uint4*>(orow + c) = v;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+static int make_qkv_tmap(CUtensorMap* tm, int dtype, const void* ptr, int B, int H, int L, int D, int ld,
+                         long long bstride, int box_rows) {
+  uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)L, (uint64_t)B};
+  uint64_t str[3] = {(uint64_t)D * 2, (uint64_t)ld * 2, (uint64_t)bstride * 2};
+  uint32_t box[4] = {(uint32_t)D, 1, (uint32_t)box_rows, 1};
+  return make_tmap(tm, dtype, 4, ptr, dims, str, box, D == 64 ? 128 : 64);
+}
+
+template <int D, bool BF16, bool HAS_BIAS>
+static int launch_fmha(const pf_fmha_args* a, cudaStream_t st) {
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = make_qkv_tmap(&tmQ, a->dtype, a->q, a->B, a->H, a->Lq, D, a->q_ld, a->q_bstride, FA_BLOCK_M))) return rc;
+  if ((rc = make_qkv_tmap(&tmK, a->dtype, a->k, a->B, a->H, a->Lk, D, a->k_ld, a->k_bstride, FA_BLOCK_N))) return rc;
+  if ((rc = make_qkv_tmap(&tmV, a->dtype, a->v, a->B, a->H, a->Lk, D, a->v_ld, a->v_bstride, FA_BLOCK_N))) return rc;
+  FmhaParams p;
+  p.B = a->B; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.out = a->out; p.out_ld = a->out_ld;
+  p.bias = a->bias; p.bias_bstride = a->bias_bstride; p.bias_ld = a->bias_ld;
+  auto kern = fmha_fwd_kernel<D, BF16, HAS_BIAS>;
+  constexpr int SMEM = fmha_smem_bytes<D>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM),
+                    "cudaFuncSetAttribute(fmha)");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  dim3 grid(((a->Lq + FA_BLOCK_M - 1) / FA_BLOCK_M) * a->H, a->B);
+  kern<<<grid, FA_THREADS, SMEM, st>>>(tmQ, tmK, tmV, p);
+  PF_CHECK_LAUNCH("fmha_fwd_kernel");
+  return PF_OK;
+}
+
+}  // namespace pf
+
+extern "C" int pf_fmha_fwd(const pf_fmha_args* a, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(a != nullptr, "pf_fmha_fwd: null args");
+  PF_CHECK_ARG(a->dtype == PF_BF16 || a->dtype == PF_F16, "pf_fmha_fwd: dtype must be PF_F16 or PF_BF16");
+  PF_CHECK_ARG(a->q && a->k && a->v && a->out, "pf_fmha_fwd: null operand");
+  PF_CHECK_ARG(a->head_dim == 32 || a->head_dim == 64, "pf_fmha_fwd: head_dim %d unsupported (32 or 64)", a->head_dim);
+  PF_CHECK_ARG(a->B > 0 && a->B <= 65535 && a->H > 0 && a->Lq > 0 && a->Lk > 0, "pf_fmha_fwd: empty shape");
+  PF_CHECK_ARG(a->q_ld % 8 == 0 && a->k_ld % 8 == 0 && a->v_ld % 8 == 0 && a->out_ld % 8 == 0,
+               "pf_fmha_fwd: leading dims must be multiples of 8 elements");
+  PF_CHECK_ARG(((uintptr_t)a->q & 15) == 0 && ((uintptr_t)a->k & 15) == 0 && ((uintptr_t)a->v & 15) == 0 &&
+                   ((uintptr_t)a->out & 15) == 0,
+               "pf_fmha_fwd: operands must be 16-byte aligned");
+  PF_CHECK_ARG(!a->bias || (a->bias_ld % 4 == 0 && ((uintptr_t)a->bias & 15) == 0 && a->bias_ld >= a->Lk),
+               "pf_fmha_fwd: bias must be 16-byte aligned with bias_ld %% 4 == 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool bf = a->dtype == PF_BF16;
+  const bool hb = a->bias != nullptr;
+  if (a->head_dim == 64) {
+    if (bf) return hb ? launch_fmha<64, true, true>(a, st) : launch_fmha<64, true, false>(a, st);
+    return hb ? launch_fmha<64, false, true>(a, st) : launch_fmha<64, false, false>(a, st);
+  }
+  if (bf) return hb ? launch_fmha<32, true, true>(a, st) : launch_fmha<32, true, false>(a, st);
+  return hb ? launch_fmha<32, false, true>(a, st) : launch_fmha<32, false, false>(a, st);
+}

@@ -1,0 +1,339 @@
+// Normalisation + convolution-input preparation kernels (HBM-bound, channels-last, 16-byte vector accesses).
+//
+//  * pf_groupnorm_stats : GroupNorm statistics of a channels-last image, optionally over the circularly padded
+//    image (the reference normalises the W+2*circ wide tensor: models/pano/MVGenModel.py:110-115 wraps every
+//    panorama ResnetBlock2D in pad_pano(2)/unpad_pano(2), so columns {0,1,W-2,W-1} count twice).
+//  * pf_conv_prep       : GroupNorm-apply (+SiLU) fused with building the tap-GEMM's A operand: circular column
+//    extension (utils/pano.py:74-105), nearest x2 upsampling (Upsample2D), zero halo, or the four stride-2
+//    phase images (Downsample2D). Replaces norm1/norm2 + nonlinearity of ResnetBlock2D, Transformer2DModel.norm,
+//    and ~60 pad_pano / unpad_pano copies per step.
+//  * pf_layernorm       : LayerNorm(x + pe) per token (models/modules/transformer.py:157-160, diffusers
+//    BasicTransformerBlock norm1/2/3).
+#include "pf_common.cuh"
+
+namespace pf {
+
+constexpr int GN_MAX_CHUNKS = 64;
+
+__device__ __forceinline__ int gn_chunks(int hw) {
+  int c = hw / 64;
+  return c < 1 ? 1 : (c > GN_MAX_CHUNKS ? GN_MAX_CHUNKS : c);
+}
+
+// partial sums: grid (chunks, N); thread <-> (8-channel vector, pixel lane)
+template <bool BF16>
+__global__ void __launch_bounds__(512)
+gn_partial_kernel(const uint16_t* __restrict__ x, int H, int W, int C, int ld, int groups, int circ,
+                  float* __restrict__ ws) {
+  extern __shared__ float s_acc[];  // [2][C]
+  const int vecs = C / 8;
+  const int ppi = blockDim.x / vecs;
+  const int v = threadIdx.x % vecs, pl = threadIdx.x / vecs;
+  const int n = blockIdx.y, chunks = gridDim.x;
+  const int hw = H * W;
+  const int per = (hw + chunks - 1) / chunks;
+  const int p_begin = blockIdx.x * per, p_end = min(hw, p_begin + per);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  if (pl < ppi) {
+    const uint16_t* base = x + (size_t)n * hw * ld + v * 8;
+    for (int p = p_begin + pl; p < p_end; p += ppi) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * ld));
+      float wgt = 1.f;
+      if (circ > 0) {
+        const int col = p % W;
+        wgt += (col < circ ? 1.f : 0.f) + (col >= W - circ ? 1.f : 0.f);
+      }
+      const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack2<BF16>(w4[e]);
+        s[2 * e] += wgt * f.x;
+        q[2 * e] += wgt * f.x * f.x;
+        s[2 * e + 1] += wgt * f.y;
+        q[2 * e + 1] += wgt * f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&s_acc[v * 8 + e], s[e]);
+      atomicAdd(&s_acc[C + v * 8 + e], q[e]);
+    }
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      a += s_acc[c];
+      b += s_acc[C + c];
+    }
+    float* o = ws + (((size_t)n * chunks + blockIdx.x) * groups + g) * 2;
+    o[0] = a;
+    o[1] = b;
+  }
+}
+
+__global__ void gn_finalize_kernel(const float* __restrict__ ws, int chunks, int groups, float count, float eps,
+                                   float* __restrict__ mean_rstd) {
+  const int n = blockIdx.x;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double a = 0.0, b = 0.0;
+    for (int c = 0; c < chunks; ++c) {
+      const float* o = ws + (((size_t)n * chunks + c) * groups + g) * 2;
+      a += o[0];
+      b += o[1];
+    }
+    const double mean = a / count;
+    double var = b / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_rstd[((size_t)n * groups + g) * 2 + 0] = float(mean);
+    mean_rstd[((size_t)n * groups + g) * 2 + 1] = float(1.0 / sqrt(var + double(eps)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_prep: thread <-> (output position, 8-channel vector)
+// ------------------------------------------------------------------------------------------------
+struct PrepParams {
+  const uint16_t* x;
+  uint16_t* out;
+  const float* mean_rstd;  // [N, groups, 2] or null (no normalisation)
+  const float* gamma;
+  const float* beta;
+  int N, H, W, C, ld, groups, act, circ, up, phases, halo;
+  int Ho, Wo;           // output positions per image (incl. halo / phase padding)
+  long long total_vecs;  // N * phases * Ho * Wo * C/8
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) conv_prep_kernel(const PrepParams p) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.total_vecs) return;
+  const int vecs = p.C / 8;
+  const int v = int(idx % vecs);
+  long long pos = idx / vecs;
+  const int j = int(pos % p.Wo);
+  pos /= p.Wo;
+  const int i = int(pos % p.Ho);
+  pos /= p.Ho;
+  const int n = int(pos % p.N);
+  const int ph = int(pos / p.N);  // phase index (0 when phases == 1)
+  // position in the (upsampled, circularly extended) image, before the zero halo
+  const int We = p.W + 2 * p.circ;
+  const int Hu = p.H * p.up, Wu = We * p.up;
+  int yy, xx;
+  if (p.phases == 4) {
+    // padded image index (2i + py, 2j + px), halo of 1 -> source (yy, xx) = that - 1
+    yy = 2 * i + (ph >> 1) - 1;
+    xx = 2 * j + (ph & 1) - 1;
+  } else {
+    yy = i - p.halo;
+    xx = j - p.halo;
+  }
+  uint4 outv = make_uint4(0, 0, 0, 0);
+  if (yy >= 0 && yy < Hu && xx >= 0 && xx < Wu) {
+    const int sy = yy / p.up;
+    int sx = xx / p.up - p.circ;
+    if (sx < 0) sx += p.W;
+    else if (sx >= p.W) sx -= p.W;
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.x + ((size_t)n * p.H * p.W + (size_t)sy * p.W + sx) * p.ld + v * 8));
+    if (p.mean_rstd || p.act) {
+      const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = unpack2<BF16>(w4[e]);
+        f[2 * e] = t.x;
+        f[2 * e + 1] = t.y;
+      }
+      if (p.mean_rstd) {
+        const int cpg = p.C / p.groups;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = v * 8 + e;
+          const int g = c / cpg;
+          const float mean = __ldg(p.mean_rstd + ((size_t)n * p.groups + g) * 2);
+          const float rstd = __ldg(p.mean_rstd + ((size_t)n * p.groups + g) * 2 + 1);
+          f[e] = (f[e] - mean) * rstd * __ldg(p.gamma + c) + __ldg(p.beta + c);
+        }
+      }
+      if (p.act == PF_ACT_SILU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
+      }
+      outv = make_uint4(pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]), pack2<BF16>(f[4], f[5]),
+                        pack2<BF16>(f[6], f[7]));
+    } else {
+      outv = raw;
+    }
+  }
+  *reinterpret_cast<uint4*>(p.out + (size_t)(idx / vecs) * p.C + v * 8) = outv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm(x + pe): one warp per token, two-pass in registers
+// ------------------------------------------------------------------------------------------------
+template <bool BF16, int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const uint16_t* __restrict__ x, int ldx, const float* __restrict__ pe, int pe_rows, int T, int C,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                 uint16_t* __restrict__ out, int ldo) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= T) return;
+  const int vecs = C / 8;
+  float f[MAXV][8];
+  float sum = 0.f;
+  const uint16_t* xr = x + (size_t)warp * ldx;
+  const float* per = pe ? pe + (size_t)(warp % pe_rows) * C : nullptr;
+#pragma unroll
+  for (int r = 0; r < MAXV; ++r) {
+    const int v = lane + r * 32;
+    if (v < vecs) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+      const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = unpack2<BF16>(w4[e]);
+        f[r][2 * e] = t.x;
+        f[r][2 * e + 1] = t.y;
+      }
+      if (per) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(per + v * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(per + v * 8 + 4));
+        f[r][0] += a.x; f[r][1] += a.y; f[r][2] += a.z; f[r][3] += a.w;
+        f[r][4] += b.x; f[r][5] += b.y; f[r][6] += b.z; f[r][7] += b.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += f[r][e];
+    }
+  }
+  const float mean = warp_sum(sum) / float(C);
+  float sq = 0.f;
+#pragma unroll
+  for (int r = 0; r < MAXV; ++r) {
+    const int v = lane + r * 32;
+    if (v < vecs) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = f[r][e] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / float(C) + eps);
+  uint16_t* orow = out + (size_t)warp * ldo;
+#pragma unroll
+  for (int r = 0; r < MAXV; ++r) {
+    const int v = lane + r * 32;
+    if (v < vecs) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = v * 8 + e;
+        o[e] = (f[r][e] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+      }
+      *reinterpret_cast<uint4*>(orow + v * 8) = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]),
+                                                           pack2<BF16>(o[4], o[5]), pack2<BF16>(o[6], o[7]));
+    }
+  }
+}
+
+}  // namespace pf
+
+extern "C" int pf_groupnorm_ws_floats(int N, int groups) { return N * pf::GN_MAX_CHUNKS * groups * 2; }
+
+extern "C" int pf_groupnorm_stats(const void* x, int dtype, int N, int H, int W, int C, int ld, int groups, int circ,
+                                  float eps, float* ws, float* mean_rstd, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(x && ws && mean_rstd, "pf_groupnorm_stats: null pointer");
+  PF_CHECK_ARG(dtype == PF_BF16 || dtype == PF_F16, "pf_groupnorm_stats: 16-bit dtype required");
+  PF_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && groups > 0 && C % groups == 0 && C % 8 == 0 && ld % 8 == 0 &&
+                   ld >= C && C / 8 <= 512,
+               "pf_groupnorm_stats: bad shape N=%d H=%d W=%d C=%d ld=%d groups=%d", N, H, W, C, ld, groups);
+  PF_CHECK_ARG(circ >= 0 && circ <= W, "pf_groupnorm_stats: circ=%d out of range", circ);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int hw = H * W;
+  int chunks = hw / 64;
+  chunks = chunks < 1 ? 1 : (chunks > GN_MAX_CHUNKS ? GN_MAX_CHUNKS : chunks);
+  const int vecs = C / 8;
+  int ppi = 256 / vecs;
+  if (ppi < 1) ppi = 1;
+  const int threads = vecs * ppi;
+  dim3 grid(chunks, N);
+  const size_t smem = 2 * (size_t)C * sizeof(float);
+  if (dtype == PF_BF16)
+    gn_partial_kernel<true><<<grid, threads, smem, st>>>(static_cast<const uint16_t*>(x), H, W, C, ld, groups, circ, ws);
+  else
+    gn_partial_kernel<false><<<grid, threads, smem, st>>>(static_cast<const uint16_t*>(x), H, W, C, ld, groups, circ, ws);
+  PF_CHECK_LAUNCH("gn_partial_kernel");
+  const float count = float(H) * float(W + 2 * circ) * float(C / groups);
+  gn_finalize_kernel<<<N, 32, 0, st>>>(ws, chunks, groups, count, eps, mean_rstd);
+  PF_CHECK_LAUNCH("gn_finalize_kernel");
+  return PF_OK;
+}
+
+extern "C" int pf_conv_prep(const void* x, void* out, int dtype, int N, int H, int W, int C, int ld,
+                            const float* mean_rstd, const float* gamma, const float* beta, int groups, int act,
+                            int circ, int up, int phases, int halo, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(x && out, "pf_conv_prep: null pointer");
+  PF_CHECK_ARG(dtype == PF_BF16 || dtype == PF_F16, "pf_conv_prep: 16-bit dtype required");
+  PF_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && ld % 8 == 0 && ld >= C, "pf_conv_prep: bad shape");
+  PF_CHECK_ARG(!mean_rstd || (gamma && beta && groups > 0 && C % groups == 0), "pf_conv_prep: GroupNorm needs gamma/beta/groups");
+  PF_CHECK_ARG(act == PF_ACT_NONE || act == PF_ACT_SILU, "pf_conv_prep: act must be none or silu");
+  PF_CHECK_ARG((up == 1 || up == 2) && (phases == 1 || phases == 4) && (halo == 0 || halo == 1) && circ >= 0 && circ <= W,
+               "pf_conv_prep: bad geometry up=%d phases=%d halo=%d circ=%d", up, phases, halo, circ);
+  PF_CHECK_ARG(!(phases == 4 && (up != 1 || halo != 1 || (H % 2) || ((W + 2 * circ) % 2))),
+               "pf_conv_prep: stride-2 phase split needs up=1, halo=1 and even extents");
+  PrepParams p;
+  p.x = static_cast<const uint16_t*>(x);
+  p.out = static_cast<uint16_t*>(out);
+  p.mean_rstd = mean_rstd; p.gamma = gamma; p.beta = beta;
+  p.N = N; p.H = H; p.W = W; p.C = C; p.ld = ld; p.groups = groups > 0 ? groups : 1; p.act = act;
+  p.circ = circ; p.up = up; p.phases = phases; p.halo = halo;
+  const int Hu = H * up, Wu = (W + 2 * circ) * up;
+  if (phases == 4) {
+    p.Ho = Hu / 2 + 1;
+    p.Wo = Wu / 2 + 1;
+  } else {
+    p.Ho = Hu + 2 * halo;
+    p.Wo = Wu + 2 * halo;
+  }
+  p.total_vecs = (long long)N * phases * p.Ho * p.Wo * (C / 8);
+  const long long blocks = (p.total_vecs + 255) / 256;
+  PF_CHECK_ARG(blocks < (1LL << 31), "pf_conv_prep: tensor too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == PF_BF16) conv_prep_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(p);
+  else conv_prep_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(p);
+  PF_CHECK_LAUNCH("conv_prep_kernel");
+  return PF_OK;
+}
+
+extern "C" int pf_layernorm(const void* x, int ldx, void* out, int ldo, int dtype, int T, int C, const float* pe,
+                            int pe_rows, const float* gamma, const float* beta, float eps, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(x && out && gamma && beta, "pf_layernorm: null pointer");
+  PF_CHECK_ARG(dtype == PF_BF16 || dtype == PF_F16, "pf_layernorm: 16-bit dtype required");
+  PF_CHECK_ARG(T > 0 && C > 0 && C % 8 == 0 && C <= 2048 && ldx % 8 == 0 && ldo % 8 == 0 && ldx >= C && ldo >= C,
+               "pf_layernorm: bad shape T=%d C=%d", T, C);
+  PF_CHECK_ARG(!pe || pe_rows > 0, "pf_layernorm: pe_rows must be positive");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = (T + 7) / 8;
+  const uint16_t* xi = static_cast<const uint16_t*>(x);
+  uint16_t* xo = static_cast<uint16_t*>(out);
+  const int rounds = (C / 8 + 31) / 32;
+#define PF_LN(BF, MV) layernorm_kernel<BF, MV><<<blocks, 256, 0, st>>>(xi, ldx, pe, pe_rows, T, C, gamma, beta, eps, xo, ldo)
+  if (dtype == PF_BF16) {
+    if (rounds <= 2) PF_LN(true, 2); else if (rounds <= 5) PF_LN(true, 5); else PF_LN(true, 8);
+  } else {
+    if (rounds <= 2) PF_LN(false, 2); else if (rounds <= 5) PF_LN(false, 5); else PF_LN(false, 8);
+  }
+#undef PF_LN
+  PF_CHECK_LAUNCH("layernorm_kernel");
+  return PF_OK;
+}

@@ -8,7 +8,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import PF_ACT_GEGLU, PF_ACT_GELU, PF_ACT_NONE, PF_ACT_SILU, GemmArgs  # noqa: F401
+from ._lib import PF_ACT_GEGLU, PF_ACT_GELU, PF_ACT_NONE, PF_ACT_SILU, FmhaArgs, GemmArgs  # noqa: F401
 
 
 def _vp(t: Optional[Tensor]):
@@ -59,4 +59,35 @@ def gemm_taps(A: Tensor, B: Tensor, out: Tensor, *, M: int, Kc: int, taps: Seque
         a.map_mode = 1
         a.Hm, a.Wm, a.i0, a.j0, a.Hout, a.Wout = (int(v) for v in image_map)
     _lib.check(_lib.lib().pf_gemm_taps(C.byref(a), _st()))
+    return out
+
+
+def fmha(q: Tensor, k: Tensor, v: Tensor, out: Tensor, *, heads: int, head_dim: int, scale: float,
+         bias: Optional[Tensor] = None) -> Tensor:
+    """out[b, l, h*d:(h+1)*d] = softmax(q_h k_h^T * scale + bias) v_h; see pf_fmha_fwd.
+
+    q: [B, Lq, >=H*d] view (last stride 1), k/v: [B, Lk, >=H*d] views — slices of a fused QKV buffer are fine.
+    bias: fp32 [Lq, Lk] (shared by batches and heads) or [B, Lq, Lk].
+    """
+    _lib.require_cuda(q, k, v, out)
+    a = FmhaArgs()
+    B, Lq = q.shape[0], q.shape[1]
+    Lk = k.shape[1]
+    for t in (q, k, v, out):
+        assert t.dim() == 3 and t.stride(2) == 1
+    a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.dtype = _lib.dtype_code(q.dtype)
+    a.B, a.H, a.Lq, a.Lk, a.head_dim = B, int(heads), Lq, Lk, int(head_dim)
+    a.q_ld, a.k_ld, a.v_ld, a.out_ld = q.stride(1), k.stride(1), v.stride(1), out.stride(1)
+    a.q_bstride, a.k_bstride, a.v_bstride = q.stride(0), k.stride(0), v.stride(0)
+    assert out.stride(0) == Lq * out.stride(1)
+    a.scale = float(scale)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.stride(-1) == 1
+        a.bias = bias.data_ptr()
+        if bias.dim() == 3:
+            a.bias_bstride, a.bias_ld = (bias.stride(0) if bias.shape[0] > 1 else 0), bias.stride(1)
+        else:
+            a.bias_bstride, a.bias_ld = 0, bias.stride(0)
+    _lib.check(_lib.lib().pf_fmha_fwd(C.byref(a), _st()))
     return out

@@ -1,0 +1,72 @@
+"""-m gpu: tcgen05 flash attention (pf_fmha_fwd) against plain PyTorch fp32 softmax(q k^T s + bias) v on the same
+16-bit-rounded inputs. The kernel rounds P to the 16-bit type before P V (like every flash kernel), so the
+tolerance is one 16-bit ulp of the output scale: fp16 rtol 1e-3 / atol 1e-3; bf16 rtol 8e-3 / atol 8e-3.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(q, k, v, heads, d, scale, bias):
+    B, Lq, _ = q.shape
+    Lk = k.shape[1]
+    sp = lambda t, L: t.float().reshape(B, L, heads, d).permute(0, 2, 1, 3)
+    s = torch.matmul(sp(q, Lq), sp(k, Lk).transpose(-1, -2)) * scale
+    if bias is not None:
+        s = s + (bias[:, None] if bias.dim() == 3 else bias[None, None])
+    o = torch.matmul(torch.softmax(s, -1), sp(v, Lk))
+    return o.permute(0, 2, 1, 3).reshape(B, Lq, heads * d)
+
+
+CASES = [
+    # B, H, Lq, Lk, d, bias
+    (2, 5, 256, 256, 64, False),
+    (16, 20, 64, 64, 64, False),     # pers 8x8 level: one ragged q tile, one ragged kv tile
+    (2, 5, 1024, 77, 64, False),     # text cross attention (77 keys)
+    (1, 5, 4096, 4096, 64, False),
+    (2, 10, 128, 512, 32, True),     # EPPA dir-1 @ 8x16 pano, 8 views of 8x8
+    (2, 10, 512, 128, 32, True),     # EPPA dir-2
+    (1, 3, 100, 77, 32, True),       # ragged both ways with bias
+    (2, 40, 300, 200, 32, False),
+    (1, 10, 2048, 2048, 32, True),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,H,Lq,Lk,d,has_bias", CASES)
+def test_fmha(cuda_device, dtype, B, H, Lq, Lk, d, has_bias):
+    from panfusion_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + Lq + Lk + d)
+    C = H * d
+    q = torch.randn(B, Lq, C, generator=g).to(dtype).to(cuda_device)
+    k = torch.randn(B, Lk, C, generator=g).to(dtype).to(cuda_device)
+    v = torch.randn(B, Lk, C, generator=g).to(dtype).to(cuda_device)
+    bias = None
+    if has_bias:
+        Lk_pad = (Lk + 3) // 4 * 4
+        bias_full = (torch.rand(Lq, Lk_pad, generator=g) * 2 - 1).to(cuda_device)
+        bias = bias_full[:, :Lk]
+    scale = 1.0 / math.sqrt(d)
+    ref = _ref(q, k, v, H, d, scale, bias)
+    out = torch.empty(B, Lq, C, dtype=dtype, device=cuda_device)
+    ops.fmha(q, k, v, out, heads=H, head_dim=d, scale=scale, bias=bias)
+    tol = dict(rtol=1e-3, atol=1e-3) if dtype == torch.float16 else dict(rtol=8e-3, atol=8e-3)
+    torch.testing.assert_close(out.float(), ref, **tol)
+
+
+def test_fmha_fused_qkv_views_and_batched_bias(cuda_device):
+    """q/k/v as column slices of one [B, L, 3C] buffer; per-batch bias."""
+    from panfusion_b200 import ops
+    B, H, L, d = 2, 10, 384, 32
+    C = H * d
+    g = torch.Generator().manual_seed(0)
+    qkv = torch.randn(B, L, 3 * C, generator=g).half().to(cuda_device)
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    bias = (torch.rand(B, L, L, generator=g) * 2 - 1).to(cuda_device)
+    ref = _ref(q, k, v, H, d, d ** -0.5, bias)
+    out = torch.empty(B, L, C, dtype=torch.float16, device=cuda_device)
+    ops.fmha(q, k, v, out, heads=H, head_dim=d, scale=d ** -0.5, bias=bias)
+    torch.testing.assert_close(out.float(), ref, rtol=1e-3, atol=1e-3)
