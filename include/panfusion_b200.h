@@ -131,6 +131,77 @@ typedef struct pf_fmha_args {
 
 int pf_fmha_fwd(const pf_fmha_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm statistics of a channels-last image x[N, H, W, C] (row stride ld), computed over the image
+ * circularly extended by `circ` columns on each side — the reference normalises the padded tensor
+ * (models/pano/MVGenModel.py:110-115 wraps each panorama ResnetBlock2D in utils/pano.py:74-105 pad/unpad), so
+ * columns {0..circ-1, W-circ..W-1} count twice. ws: scratch of pf_groupnorm_ws_floats(N, groups) floats.
+ * mean_rstd: [N, groups, 2] fp32 (mean, 1/sqrt(var + eps)), biased variance like torch.nn.GroupNorm.
+ * ------------------------------------------------------------------------------------------------ */
+int pf_groupnorm_ws_floats(int N, int groups);
+int pf_groupnorm_stats(const void* x, int dtype, int N, int H, int W, int C, int ld, int groups, int circ,
+                       float eps, float* ws, float* mean_rstd, void* stream);
+
+/* GroupNorm-apply (+SiLU) fused with building the tap-GEMM A operand (replaces norm+nonlinearity of diffusers
+ * ResnetBlock2D / Transformer2DModel.norm, pad_pano/unpad_pano utils/pano.py:74-105, Upsample2D's nearest x2,
+ * Downsample2D's stride-2 gather; call sites MVGenModel.py:98-277).
+ *   source image S = x circularly extended by `circ` columns per side, then nearest-upsampled by `up` (1|2);
+ *   phases == 1: out[N, Hu + 2*halo, Wu + 2*halo, C], zero halo (halo = 1 for a 3x3 conv input, 0 = plain apply)
+ *   phases == 4: out[4][N][Hu/2 + 1][Wu/2 + 1][C], phase (py,px) element (i,j) = zero-padded S at (2i+py, 2j+px)
+ * mean_rstd == NULL skips the normalisation; act: PF_ACT_NONE | PF_ACT_SILU. */
+int pf_conv_prep(const void* x, void* out, int dtype, int N, int H, int W, int C, int ld, const float* mean_rstd,
+                 const float* gamma, const float* beta, int groups, int act, int circ, int up, int phases, int halo,
+                 void* stream);
+
+/* out[t, :] = LayerNorm(x[t, :] + pe[t % pe_rows, :]) * gamma + beta (pe fp32, may be NULL);
+ * models/modules/transformer.py:157-160 (EPPA norm1 on x + query_pe / context, norm2) and the diffusers
+ * BasicTransformerBlock norm1/2/3. */
+int pf_layernorm(const void* x, int ldx, void* out, int ldo, int dtype, int T, int C, const float* pe, int pe_rows,
+                 const float* gamma, const float* beta, float eps, void* stream);
+
+/* conv_in (MVGenModel.py:85-91): NCHW fp32 latent [N,Cin,H,W] -> tokens [N*H*W, Cout] 16-bit; 3x3 pad 1;
+ * circ != 0 wraps columns (== pad_pano(1) -> conv -> unpad_pano(1)). w fp32 [Cout,Cin,3,3], bias fp32 [Cout]. */
+int pf_conv_in(const float* x, const float* w, const float* bias, void* out, int dtype, int N, int Cin, int H, int W,
+               int Cout, int circ, void* stream);
+
+/* conv_norm_out -> SiLU -> conv_out (MVGenModel.py:279-295): tokens [N,H,W,C] 16-bit -> NCHW fp32 [N,Cout<=4,H,W];
+ * mean_rstd from pf_groupnorm_stats (circ = 0: the reference normalises the un-padded tensor at :288). */
+int pf_conv_out(const void* x, int ld, int dtype, const float* mean_rstd, const float* gamma, const float* beta,
+                int groups, const float* w, const float* bias, float* out, int N, int H, int W, int C, int Cout,
+                int circ, void* stream);
+
+/* strided 2-D copy of 16-bit rows (skip concatenation, torch.cat at MVGenModel.py:223,231,246,254) */
+int pf_copy2d(const void* src, int src_ld, void* dst, int dst_ld, long long rows, int cols, void* stream);
+
+/* diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0) (MVGenModel.py:55,59): t fp32 [n] -> [n, dim] */
+int pf_timestep_embed(const float* t, void* out, int dtype, int n, int dim, void* stream);
+
+/* Classifier-free-guidance combine + DDIM update (+ roll of the result by `roll` columns):
+ *   e = eps[0:count] + guidance * (eps[count:2count] - eps[0:count])        (PanoGenerator.py:253-262)
+ *   out[.., (col+roll) % W] = sqrt(a_prev) * (x - sqrt(1-a_t) e) / sqrt(a_t) + sqrt(1-a_prev) e   (DDIM, eta 0)
+ * replaces combine_cls_free_guide_pred + DDIMScheduler.step (PanFusion.py:159-162) + torch.roll
+ * (PanoGenerator.py:264-269) of the following step. x, out fp32 [count] viewed as rows of W. */
+int pf_cfg_ddim_step(const float* x, const float* eps, float* out, long long count, int W, int roll, float guidance,
+                     float alpha_t, float alpha_prev, void* stream);
+/* same update with the two coefficients read from DEVICE memory: coef[0] = sqrt(a_prev/a_t),
+ * coef[1] = sqrt(1-a_prev) - coef[0]*sqrt(1-a_t) — lets one captured CUDA graph serve every denoising step. */
+int pf_cfg_ddim_step_dev(const float* x, const float* eps, float* out, long long count, int W, int roll,
+                         float guidance, const float* coef, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * EPPA geometry tables (models/pano/utils.py:10-106, models/modules/transformer.py:185-201).
+ * pf_eppa_tables: correspondence bias for both attention directions of V views (groups of m views per batch
+ * element) straight from the camera records (device, PF_CAM_DOUBLES each; e2p and p2e flavours):
+ *   bias1[V/m][eh*ew][m*ph*pw]  query = pano pixel, keys = view pixels   (modules.py:46)
+ *   bias2[V/m][m*ph*pw][eh*ew]  query = view pixel, keys = pano pixels   (modules.py:53)
+ * blur5: HOST pointer to the 5 taps of the sigma-1 gaussian. ws_idx / ws_w: scratch of 4*V*(ph*pw+eh*ew) each.
+ * pf_eppa_pe: SphericalPE tables, fp32: pers_pe[V*ph*pw][4*n_freqs], equi_pe[eh*ew][4*n_freqs].
+ * ------------------------------------------------------------------------------------------------ */
+int pf_eppa_tables(const double* cams_e2p, const double* cams_p2e, int V, int m, int ph, int pw, int eh, int ew,
+                   const float* blur5, int* ws_idx, float* ws_w, float* bias1, float* bias2, void* stream);
+int pf_eppa_pe(const double* cams_e2p, int V, int ph, int pw, int eh, int ew, const float* freq_bands, int n_freqs,
+               float* pers_pe, float* equi_pe, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,10 +118,11 @@ class FeedForward(nn.Module):  # transformer.py:18-38 (glu=True branch is the on
     def __init__(self, dim, mult=4):
         super().__init__()
         inner = int(dim * mult)
+        proj = GEGLU(dim, inner)  # created first so seeded initialisation matches the reference's draw order
         out = nn.Linear(inner, dim)
         nn.init.zeros_(out.weight)
         nn.init.zeros_(out.bias)
-        self.net = nn.Sequential(GEGLU(dim, inner), nn.Dropout(0.0), out)
+        self.net = nn.Sequential(proj, nn.Dropout(0.0), out)
 
     def forward(self, x):
         return self.net(x)

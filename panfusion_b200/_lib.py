@@ -74,6 +74,9 @@ EXPORTS = [
     "pf_e2p", "pf_p2e",
     "pf_gemm_taps", "pf_gemm_pick_block_n",
     "pf_fmha_fwd",
+    "pf_groupnorm_ws_floats", "pf_groupnorm_stats", "pf_conv_prep", "pf_layernorm",
+    "pf_conv_in", "pf_conv_out", "pf_copy2d", "pf_timestep_embed", "pf_cfg_ddim_step", "pf_cfg_ddim_step_dev",
+    "pf_eppa_tables", "pf_eppa_pe",
 ]
 
 

@@ -141,9 +141,13 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t, uint16_t* __r
 // PanoGenerator.py:264-269. eps holds [uncond | text] halves of `count` elements each; x, out are [rows, W] fp32.
 __global__ void __launch_bounds__(256)
 cfg_ddim_kernel(const float* __restrict__ x, const float* __restrict__ eps, float* __restrict__ out, long long count,
-                int W, int roll, float guidance, float c_x, float c_eps) {
+                int W, int roll, float guidance, float c_x, float c_eps, const float* __restrict__ coef_dev) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= count) return;
+  if (coef_dev) {  // coefficients read from device memory so a captured CUDA graph can be replayed for any step
+    c_x = coef_dev[0];
+    c_eps = coef_dev[1];
+  }
   const float eu = eps[idx], ec = eps[count + idx];
   const float e = eu + guidance * (ec - eu);
   const float v = c_x * x[idx] + c_eps * e;
@@ -238,7 +242,17 @@ extern "C" int pf_cfg_ddim_step(const float* x, const float* eps, float* out, lo
   const float c_x = (float)sa;
   const float c_eps = (float)(sqrt(1.0 - (double)alpha_prev) - sa * sqrt(1.0 - (double)alpha_t));
   cfg_ddim_kernel<<<(unsigned)((count + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, eps, out, count, W, roll, guidance, c_x, c_eps);
+      x, eps, out, count, W, roll, guidance, c_x, c_eps, nullptr);
+  PF_CHECK_LAUNCH("cfg_ddim_kernel");
+  return PF_OK;
+}
+
+extern "C" int pf_cfg_ddim_step_dev(const float* x, const float* eps, float* out, long long count, int W, int roll,
+                                    float guidance, const float* coef, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(x && eps && out && coef && count > 0 && W > 0 && count % W == 0, "pf_cfg_ddim_step_dev: bad arguments");
+  cfg_ddim_kernel<<<(unsigned)((count + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, eps, out, count, W, roll, guidance, 0.f, 0.f, coef);
   PF_CHECK_LAUNCH("cfg_ddim_kernel");
   return PF_OK;
 }

@@ -25,7 +25,7 @@ template <bool BF16>
 __global__ void __launch_bounds__(512)
 gn_partial_kernel(const uint16_t* __restrict__ x, int H, int W, int C, int ld, int groups, int circ,
                   float* __restrict__ ws) {
-  extern __shared__ float s_acc[];  // [2][C]
+  extern __shared__ float s_acc[];  // [ppi][2][C] per-pixel-lane partials (fixed-order reduction: deterministic)
   const int vecs = C / 8;
   const int ppi = blockDim.x / vecs;
   const int v = threadIdx.x % vecs, pl = threadIdx.x / vecs;
@@ -33,12 +33,10 @@ gn_partial_kernel(const uint16_t* __restrict__ x, int H, int W, int C, int ld, i
   const int hw = H * W;
   const int per = (hw + chunks - 1) / chunks;
   const int p_begin = blockIdx.x * per, p_end = min(hw, p_begin + per);
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
-  if (pl < ppi) {
+  {
     const uint16_t* base = x + (size_t)n * hw * ld + v * 8;
     for (int p = p_begin + pl; p < p_end; p += ppi) {
       const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * ld));
@@ -57,11 +55,18 @@ gn_partial_kernel(const uint16_t* __restrict__ x, int H, int W, int C, int ld, i
         q[2 * e + 1] += wgt * f.y * f.y;
       }
     }
+    float* mine = s_acc + (size_t)pl * 2 * C;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      atomicAdd(&s_acc[v * 8 + e], s[e]);
-      atomicAdd(&s_acc[C + v * 8 + e], q[e]);
+      mine[v * 8 + e] = s[e];
+      mine[C + v * 8 + e] = q[e];
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float a = s_acc[i];
+    for (int l = 1; l < ppi; ++l) a += s_acc[(size_t)l * 2 * C + i];
+    s_acc[i] = a;
   }
   __syncthreads();
   const int cpg = C / groups;
@@ -265,7 +270,7 @@ extern "C" int pf_groupnorm_stats(const void* x, int dtype, int N, int H, int W,
   if (ppi < 1) ppi = 1;
   const int threads = vecs * ppi;
   dim3 grid(chunks, N);
-  const size_t smem = 2 * (size_t)C * sizeof(float);
+  const size_t smem = 2 * (size_t)C * ppi * sizeof(float);
   if (dtype == PF_BF16)
     gn_partial_kernel<true><<<grid, threads, smem, st>>>(static_cast<const uint16_t*>(x), H, W, C, ld, groups, circ, ws);
   else

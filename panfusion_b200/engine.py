@@ -1,0 +1,306 @@
+"""Host-side engine: packs the weights of a duck-typed SD-2 `UNet2DConditionModel` once and runs its blocks as
+sequences of C-ABI kernel launches on channels-last 16-bit activations.
+
+The reference never calls `unet.forward`; it walks the sub-modules (models/pano/MVGenModel.py:52-295). This file is
+the per-sub-module replacement for that walk: `resnet`, `transformer`, `downsample`, `upsample`, `conv_in`,
+`conv_out` take and return `Img` activations ([N*H*W, C] tokens) and issue only `panfusion_b200.ops` calls.
+Semantics follow diffusers 0.24.0 ResnetBlock2D / Transformer2DModel / Downsample2D / Upsample2D [3P] with the
+panorama branch's circular padding (utils/pano.py:74-105) folded into the kernels.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import ops
+from .packing import pack_conv3x3, pack_geglu
+
+
+@dataclass
+class Img:
+    """Channels-last activation: t is [N*H*W, C] (row stride may exceed C)."""
+    t: Tensor
+    N: int
+    H: int
+    W: int
+
+    @property
+    def C(self) -> int:
+        return self.t.shape[1]
+
+    def nchw(self) -> Tensor:
+        return self.t.reshape(self.N, self.H, self.W, self.C).permute(0, 3, 1, 2)
+
+
+def img_from_nchw(x: Tensor, dtype: torch.dtype) -> Img:
+    n, c, h, w = x.shape
+    return Img(x.permute(0, 2, 3, 1).reshape(n * h * w, c).to(dtype).contiguous(), n, h, w)
+
+
+def taps3x3(row_pitch: int) -> list[int]:
+    return [(dy - 1) * row_pitch + (dx - 1) for dy in range(3) for dx in range(3)]
+
+
+class _Lin:
+    """Packed nn.Linear / 1x1 conv: W [N, K] 16-bit, bias fp32."""
+
+    def __init__(self, w: Tensor, b: Optional[Tensor], dev, dt):
+        self.w = w.detach().reshape(w.shape[0], -1).to(dev, dt).contiguous()
+        self.b = b.detach().to(dev, torch.float32).contiguous() if b is not None else None
+        self.n, self.k = self.w.shape
+
+
+class _Norm:
+    def __init__(self, mod, dev):
+        self.g = mod.weight.detach().to(dev, torch.float32).contiguous()
+        self.b = mod.bias.detach().to(dev, torch.float32).contiguous()
+        self.eps = float(mod.eps)
+        self.groups = int(getattr(mod, "num_groups", 0))
+
+
+class _Conv3:
+    def __init__(self, conv, dev, dt):
+        self.w = pack_conv3x3(conv.weight.detach()).to(dev, dt).contiguous()
+        self.b = conv.bias.detach().to(dev, torch.float32).contiguous() if conv.bias is not None else None
+        self.cout, self.cin = conv.weight.shape[0], conv.weight.shape[1]
+
+
+class _Resnet:
+    def __init__(self, r, dev, dt):
+        self.norm1, self.norm2 = _Norm(r.norm1, dev), _Norm(r.norm2, dev)
+        self.conv1, self.conv2 = _Conv3(r.conv1, dev, dt), _Conv3(r.conv2, dev, dt)
+        self.short = _Lin(r.conv_shortcut.weight, r.conv_shortcut.bias, dev, dt) if getattr(r, "conv_shortcut", None) is not None else None
+        self.temb_off = -1  # column offset into the per-forward temb projection table
+
+
+class _Transformer:
+    def __init__(self, t, dev, dt):
+        blk = t.transformer_blocks[0]
+        assert len(t.transformer_blocks) == 1
+        self.norm = _Norm(t.norm, dev)
+        self.proj_in = _Lin(t.proj_in.weight, t.proj_in.bias, dev, dt)
+        self.proj_out = _Lin(t.proj_out.weight, t.proj_out.bias, dev, dt)
+        self.heads = int(blk.attn1.heads)
+        self.ln1, self.ln2, self.ln3 = _Norm(blk.norm1, dev), _Norm(blk.norm2, dev), _Norm(blk.norm3, dev)
+        a1, a2 = blk.attn1, blk.attn2
+        self.qkv = _Lin(torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0), None, dev, dt)
+        self.out1 = _Lin(a1.to_out[0].weight, a1.to_out[0].bias, dev, dt)
+        self.q2 = _Lin(a2.to_q.weight, None, dev, dt)
+        self.kv2_w = torch.cat([a2.to_k.weight, a2.to_v.weight], 0).detach()  # merged across layers by UNetPack
+        self.out2 = _Lin(a2.to_out[0].weight, a2.to_out[0].bias, dev, dt)
+        self.kv_off = -1
+        ff1, ff2 = blk.ff.net[0].proj, blk.ff.net[2]
+        self.ff1_bn = ops.pick_block_n(ff1.weight.shape[0], ops.PF_ACT_GEGLU)
+        wp, bp = pack_geglu(ff1.weight.detach(), ff1.bias.detach(), self.ff1_bn)
+        self.ff1_w, self.ff1_b = wp.to(dev, dt).contiguous(), bp.to(dev)
+        self.ff2 = _Lin(ff2.weight, ff2.bias, dev, dt)
+        self.C = self.proj_in.n
+
+
+class UNetPack:
+    """All weights of one UNet, packed for the kernels; built once per (device, dtype)."""
+
+    def __init__(self, unet, dev, dt):
+        self.dev, self.dt = dev, dt
+        self.groups = int(unet.conv_norm_out.num_groups)
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        self.conv_in_w, self.conv_in_b = f32(unet.conv_in.weight), f32(unet.conv_in.bias)
+        self.conv_out_w, self.conv_out_b = f32(unet.conv_out.weight), f32(unet.conv_out.bias)
+        self.norm_out = _Norm(unet.conv_norm_out, dev)
+        te = unet.time_embedding
+        self.t_dim = te.linear_1.weight.shape[1]
+        self.te1, self.te2 = _Lin(te.linear_1.weight, te.linear_1.bias, dev, dt), _Lin(te.linear_2.weight, te.linear_2.bias, dev, dt)
+        self.resnets: list[_Resnet] = []
+        self.transformers: list[_Transformer] = []
+
+        def res(r):
+            p = _Resnet(r, dev, dt)
+            p._src = r
+            self.resnets.append(p)
+            return p
+
+        def tr(t):
+            p = _Transformer(t, dev, dt)
+            self.transformers.append(p)
+            return p
+
+        self.down = []
+        for blk in unet.down_blocks:
+            has_attn = bool(getattr(blk, "has_cross_attention", False))
+            self.down.append(dict(
+                resnets=[res(r) for r in blk.resnets],
+                attns=[tr(t) for t in blk.attentions] if has_attn else None,
+                down=[_Conv3(d.conv, dev, dt) for d in blk.downsamplers] if blk.downsamplers is not None else None))
+        self.mid = dict(resnets=[res(r) for r in unet.mid_block.resnets], attns=[tr(t) for t in unet.mid_block.attentions])
+        self.up = []
+        for blk in unet.up_blocks:
+            has_attn = bool(getattr(blk, "has_cross_attention", False))
+            self.up.append(dict(
+                resnets=[res(r) for r in blk.resnets],
+                attns=[tr(t) for t in blk.attentions] if has_attn else None,
+                up=[_Conv3(u.conv, dev, dt) for u in blk.upsamplers] if blk.upsamplers is not None else None))
+        # one GEMM for every ResnetBlock2D.time_emb_proj (applied to silu(temb))
+        off, ws, bs = 0, [], []
+        for p in self.resnets:
+            p.temb_off = off
+            ws.append(p._src.time_emb_proj.weight.detach())
+            bs.append(p._src.time_emb_proj.bias.detach())
+            off += p.conv1.cout
+            del p._src
+        self.temb_all = _Lin(torch.cat(ws, 0), torch.cat(bs, 0), dev, dt)
+        # one GEMM for every text cross-attention K/V projection
+        off, ws = 0, []
+        for t in self.transformers:
+            t.kv_off = off
+            ws.append(t.kv2_w)
+            off += t.kv2_w.shape[0]
+            del t.kv2_w
+        self.kv_all = _Lin(torch.cat(ws, 0), None, dev, dt) if ws else None
+
+
+class Branch:
+    """One UNet branch (perspective or panorama) bound to its per-forward context (temb table, text K/V)."""
+
+    def __init__(self, pack: UNetPack, circular: bool):
+        self.p = pack
+        self.circ = circular  # panorama branch with pano_pad=True
+        self.dt = pack.dt
+        self.temb: Optional[Tensor] = None   # [N, sum(Cout)] fp32
+        self.text_kv: Optional[Tensor] = None  # [N, 77, sum(2C)]
+        self._text_key = None
+
+    # ---- per-forward context ---------------------------------------------------------------------
+    def set_timesteps(self, t: Tensor) -> None:
+        """time_proj -> time_embedding -> every time_emb_proj(silu(.)) (MVGenModel.py:52-60 + ResnetBlock2D)."""
+        p = self.p
+        t = t.reshape(-1).to(torch.float32)
+        n = t.numel()
+        e0 = ops.timestep_embed(t, p.t_dim, self.dt)
+        e1 = torch.empty((n, p.te1.n), dtype=self.dt, device=p.dev)
+        ops.gemm_taps(e0, p.te1.w, e1, M=n, Kc=p.te1.k, bias=p.te1.b, act=ops.PF_ACT_SILU)
+        e2 = torch.empty((n, p.te2.n), dtype=self.dt, device=p.dev)
+        ops.gemm_taps(e1, p.te2.w, e2, M=n, Kc=p.te2.k, bias=p.te2.b, act=ops.PF_ACT_SILU)  # = silu(temb)
+        self.temb = torch.empty((n, p.temb_all.n), dtype=torch.float32, device=p.dev)
+        ops.gemm_taps(e2, p.temb_all.w, self.temb, M=n, Kc=p.temb_all.k, bias=p.temb_all.b)
+
+    def set_text(self, prompt: Tensor, key=None) -> None:
+        """prompt [N, L, ctx] -> K/V of every cross-attention layer. The text does not change across denoising steps
+        (PanFusion.py:134-138 embeds it once), so the result is cached on the identity + version of the caller's
+        tensor (`key`, taken before any slicing/reshaping)."""
+        key = key if key is not None else (prompt.data_ptr(), prompt._version, tuple(prompt.shape))
+        if key == self._text_key:
+            return
+        p = self.p
+        n, L, ctx = prompt.shape
+        x = prompt.reshape(n * L, ctx).to(self.dt).contiguous()
+        kv = torch.empty((n * L, p.kv_all.n), dtype=self.dt, device=p.dev)
+        ops.gemm_taps(x, p.kv_all.w, kv, M=n * L, Kc=ctx)
+        self.text_kv = kv.reshape(n, L, p.kv_all.n)
+        self._text_key = key
+
+    # ---- blocks ------------------------------------------------------------------------------------
+    def conv_in(self, latent: Tensor) -> Img:
+        n, _, h, w = latent.shape
+        t = ops.conv_in(latent.to(torch.float32).contiguous(), self.p.conv_in_w, self.p.conv_in_b, self.dt, self.circ)
+        return Img(t, n, h, w)
+
+    def conv_out(self, x: Img) -> Tensor:
+        p = self.p
+        stats = ops.groupnorm_stats(x.t, x.N, x.H, x.W, p.groups, p.norm_out.eps, 0)  # un-padded (MVGenModel.py:288)
+        return ops.conv_out(x.t, x.N, x.H, x.W, stats, p.norm_out.g, p.norm_out.b, p.groups, p.conv_out_w,
+                            p.conv_out_b, self.circ)
+
+    def resnet(self, x: Img, r: _Resnet) -> Img:
+        """ResnetBlock2D; panorama: pad_pano(2) -> block -> unpad_pano(2) (MVGenModel.py:110-115)."""
+        c = 2 if self.circ else 0
+        N, H, W = x.N, x.H, x.W
+        We = W + 2 * c
+        g = self.p.groups
+        s1 = ops.groupnorm_stats(x.t, N, H, W, g, r.norm1.eps, c)
+        a1 = ops.conv_prep(x.t, N, H, W, stats=s1, gamma=r.norm1.g, beta=r.norm1.b, groups=g, act=ops.PF_ACT_SILU,
+                           circ=c, halo=1)
+        Hp, Wp = H + 2, We + 2
+        h1 = torch.empty((N * H * We, r.conv1.cout), dtype=self.dt, device=x.t.device)
+        ops.gemm_taps(a1, r.conv1.w, h1, M=N * Hp * Wp, Kc=r.conv1.cin, taps=taps3x3(Wp), bias=r.conv1.b,
+                      rowbias=self.temb[:, r.temb_off:r.temb_off + r.conv1.cout], image_map=(Hp, Wp, 1, 1, H, We))
+        s2 = ops.groupnorm_stats(h1, N, H, We, g, r.norm2.eps, 0)  # the padded-width tensor, borders included
+        a2 = ops.conv_prep(h1, N, H, We, stats=s2, gamma=r.norm2.g, beta=r.norm2.b, groups=g, act=ops.PF_ACT_SILU,
+                           circ=0, halo=1)
+        if r.short is not None:
+            res = torch.empty((N * H * W, r.short.n), dtype=self.dt, device=x.t.device)
+            ops.gemm_taps(x.t, r.short.w, res, M=N * H * W, Kc=r.short.k, bias=r.short.b)
+        else:
+            res = x.t
+        out = torch.empty((N * H * W, r.conv2.cout), dtype=self.dt, device=x.t.device)
+        ops.gemm_taps(a2, r.conv2.w, out, M=N * Hp * Wp, Kc=r.conv2.cin, taps=taps3x3(Wp), bias=r.conv2.b,
+                      residual=res, image_map=(Hp, Wp, 1, 1 + c, H, W))
+        return Img(out, N, H, W)
+
+    def transformer(self, x: Img, t: _Transformer) -> Img:
+        """Transformer2DModel (GroupNorm -> proj_in -> self-attn -> text cross-attn -> GEGLU FF -> proj_out + x)."""
+        N, H, W, C = x.N, x.H, x.W, t.C
+        L, T = H * W, N * H * W
+        dev, dt = x.t.device, self.dt
+        new = lambda n: torch.empty((T, n), dtype=dt, device=dev)
+        s = ops.groupnorm_stats(x.t, N, H, W, self.p.groups, t.norm.eps, 0)
+        xn = ops.conv_prep(x.t, N, H, W, stats=s, gamma=t.norm.g, beta=t.norm.b, groups=self.p.groups, halo=0)
+        h = ops.gemm_taps(xn, t.proj_in.w, new(C), M=T, Kc=t.proj_in.k, bias=t.proj_in.b)
+        d = C // t.heads
+        # self attention
+        n1 = ops.layernorm(h, t.ln1.g, t.ln1.b, t.ln1.eps)
+        qkv = ops.gemm_taps(n1, t.qkv.w, new(3 * C), M=T, Kc=C).reshape(N, L, 3 * C)
+        o = torch.empty((N, L, C), dtype=dt, device=dev)
+        ops.fmha(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], o, heads=t.heads, head_dim=d, scale=d ** -0.5)
+        h = ops.gemm_taps(o.reshape(T, C), t.out1.w, new(C), M=T, Kc=C, bias=t.out1.b, residual=h)
+        # text cross attention (K/V precomputed by set_text)
+        n2 = ops.layernorm(h, t.ln2.g, t.ln2.b, t.ln2.eps)
+        q = ops.gemm_taps(n2, t.q2.w, new(C), M=T, Kc=C).reshape(N, L, C)
+        kv = self.text_kv
+        ops.fmha(q, kv[..., t.kv_off:t.kv_off + C], kv[..., t.kv_off + C:t.kv_off + 2 * C], o, heads=t.heads,
+                 head_dim=d, scale=d ** -0.5)
+        h = ops.gemm_taps(o.reshape(T, C), t.out2.w, new(C), M=T, Kc=C, bias=t.out2.b, residual=h)
+        # feed-forward
+        n3 = ops.layernorm(h, t.ln3.g, t.ln3.b, t.ln3.eps)
+        f = ops.gemm_taps(n3, t.ff1_w, new(t.ff2.k), M=T, Kc=C, bias=t.ff1_b, act=ops.PF_ACT_GEGLU, block_n=t.ff1_bn)
+        h = ops.gemm_taps(f, t.ff2.w, new(C), M=T, Kc=t.ff2.k, bias=t.ff2.b, residual=h)
+        out = ops.gemm_taps(h, t.proj_out.w, new(x.C), M=T, Kc=C, bias=t.proj_out.b, residual=x.t)
+        return Img(out, N, H, W)
+
+    def downsample(self, x: Img, d: _Conv3) -> Img:
+        """Downsample2D (3x3, stride 2, pad 1); panorama: pad_pano(2) -> conv -> unpad_pano(1) (MVGenModel.py:139-144)."""
+        c = 2 if self.circ else 0
+        N, H, W = x.N, x.H, x.W
+        We = W + 2 * c
+        a = ops.conv_prep(x.t, N, H, W, circ=c, phases=4, halo=1)
+        Ho, Wo = H // 2, We // 2
+        Hq, Wq = Ho + 1, Wo + 1
+        PS = N * Hq * Wq
+        taps = [((dy % 2) * 2 + (dx % 2)) * PS + (dy // 2) * Wq + (dx // 2) for dy in range(3) for dx in range(3)]
+        crop = 1 if self.circ else 0
+        Wout = Wo - 2 * crop
+        out = torch.empty((N * Ho * Wout, d.cout), dtype=self.dt, device=x.t.device)
+        ops.gemm_taps(a, d.w, out, M=PS, Kc=d.cin, taps=taps, bias=d.b, image_map=(Hq, Wq, 0, crop, Ho, Wout))
+        return Img(out, N, Ho, Wout)
+
+    def upsample(self, x: Img, u: _Conv3) -> Img:
+        """Upsample2D (nearest x2 -> 3x3 conv); panorama: pad_pano(1) -> up -> unpad_pano(2) (MVGenModel.py:272-277)."""
+        c = 1 if self.circ else 0
+        N, H, W = x.N, x.H, x.W
+        a = ops.conv_prep(x.t, N, H, W, circ=c, up=2, halo=1)
+        Hu, Wu = 2 * H, 2 * (W + 2 * c)
+        Hp, Wp = Hu + 2, Wu + 2
+        out = torch.empty((N * Hu * 2 * W, u.cout), dtype=self.dt, device=x.t.device)
+        ops.gemm_taps(a, u.w, out, M=N * Hp * Wp, Kc=u.cin, taps=taps3x3(Wp), bias=u.b,
+                      image_map=(Hp, Wp, 1, 1 + 2 * c, Hu, 2 * W))
+        return Img(out, N, Hu, 2 * W)
+
+    def concat(self, a: Img, b: Img) -> Img:
+        """torch.cat([hidden, skip], dim=1) in channels-last layout."""
+        T = a.t.shape[0]
+        out = torch.empty((T, a.C + b.C), dtype=self.dt, device=a.t.device)
+        ops.copy2d(a.t, out[:, :a.C])
+        ops.copy2d(b.t, out[:, a.C:])
+        return Img(out, a.N, a.H, a.W)

@@ -1,0 +1,173 @@
+"""`MultiViewBaseModel` behind the reference's interface (models/pano/MVGenModel.py:8-297).
+
+Same constructor `(unet, pano_unet, pers_cn=None, pano_cn=None, pano_pad=True)`, same attributes (`unet`,
+`pano_unet`, `cp_blocks_encoder`, `cp_blocks_mid`, `cp_blocks_decoder`, `trainable_parameters`), same forward
+signature and return value. The UNets are consumed by attribute walk exactly like the reference does, but only to
+READ their parameters once (engine.UNetPack); every block then runs as hand-written sm_100a kernels on
+channels-last 16-bit activations. There is no PyTorch fallback: without a CUDA device / the built library the
+forward raises.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import _lib
+from .engine import Branch, Img, UNetPack
+from .eppa import CameraTables, WarpAttn
+
+
+class MultiViewBaseModel(nn.Module):
+    def __init__(self, unet, pano_unet, pers_cn=None, pano_cn=None, pano_pad=True, compute_dtype=torch.bfloat16):
+        super().__init__()
+        self.unet = unet
+        self.pano_unet = pano_unet
+        self.pers_cn = pers_cn
+        self.pano_cn = pano_cn
+        self.pano_pad = pano_pad
+        self.compute_dtype = compute_dtype
+        if self.unet is not None:  # MVGenModel.py:17-36
+            self.cp_blocks_encoder = nn.ModuleList(
+                [WarpAttn(blk.downsamplers[-1].out_channels) for blk in unet.down_blocks if blk.downsamplers is not None])
+            self.cp_blocks_mid = WarpAttn(unet.mid_block.resnets[-1].out_channels)
+            self.cp_blocks_decoder = nn.ModuleList(
+                [WarpAttn(blk.upsamplers[0].channels) for blk in unet.up_blocks if blk.upsamplers is not None])
+            self.trainable_parameters = [(list(self.cp_blocks_mid.parameters())
+                                          + list(self.cp_blocks_decoder.parameters())
+                                          + list(self.cp_blocks_encoder.parameters()), 1.0)]
+            tables = CameraTables()
+            for w in [*self.cp_blocks_encoder, self.cp_blocks_mid, *self.cp_blocks_decoder]:
+                w.tables = tables
+        self._branches = None
+        self._par = None
+
+    def set_view_parallel(self, group=None, batch_shards=None, view_shards=None) -> None:
+        """Shard the step over the ranks of `group` (parallel.ViewParallel): CFG halves first, then views."""
+        from .parallel import ViewParallel
+        self._par = ViewParallel(group, batch_shards, view_shards)
+
+    # ---- packing -----------------------------------------------------------------------------------
+    def prepare(self, device=None, dtype=None) -> "MultiViewBaseModel":
+        """Pack all weights for the kernels (call again after loading new weights)."""
+        device = torch.device(device or "cuda")
+        dtype = dtype or self.compute_dtype
+        _lib.check(_lib.lib().pf_check_device())
+        pers = Branch(UNetPack(self.unet, device, dtype), circular=False) if self.unet is not None else None
+        pano = Branch(UNetPack(self.pano_unet, device, dtype), circular=bool(self.pano_pad))
+        self._branches = (pers, pano, device, dtype)
+        if self.unet is not None:
+            for w in [*self.cp_blocks_encoder, self.cp_blocks_mid, *self.cp_blocks_decoder]:
+                w.invalidate()
+        return self
+
+    def invalidate(self):
+        self._branches = None
+
+    # ---- forward -----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, latents: Optional[Tensor], pano_latent: Tensor, timestep: Tensor, prompt_embd: Optional[Tensor],
+                pano_prompt_embd: Tensor, cameras: Optional[dict], pers_layout_cond=None, pano_layout_cond=None):
+        if (self.pers_cn is not None and pers_layout_cond is not None) or \
+                (self.pano_cn is not None and pano_layout_cond is not None):
+            raise NotImplementedError("ControlNet residuals (MVGenModel.py:62-83) are not on the sm_100a path yet")
+        _lib.require_cuda(pano_latent)
+        if self._branches is None or self._branches[2] != pano_latent.device:
+            self.prepare(pano_latent.device)
+        pers, pano, dev, dt = self._branches
+        has_pers = pers is not None
+
+        tkey = lambda t, tag: (t.data_ptr(), t._version, tuple(t.shape), tag)
+        text_key = tkey(prompt_embd, "pers") if prompt_embd is not None else None
+        pano_text_key = tkey(pano_prompt_embd, "pano")
+        par = self._par if has_pers else None
+        if par is not None:
+            # keep this rank's CFG/batch elements and views; cameras of ALL views stay (EPPA bias needs them)
+            b_full, m_full = latents.shape[:2]
+            par.configure(b_full, m_full)
+            bsl, vsl = par.slices(b_full, m_full)
+            latents, timestep, prompt_embd = latents[bsl, vsl], timestep[bsl, vsl], prompt_embd[bsl, vsl]
+            pano_latent, pano_prompt_embd = pano_latent[bsl], pano_prompt_embd[bsl]
+            cameras = {k: v[bsl] for k, v in cameras.items()}
+        if has_pers:
+            b, m = latents.shape[:2]
+            cam_key = CameraTables.camera_key({k: v.flatten(0, 1) for k, v in cameras.items()})
+            pers.set_timesteps(timestep.reshape(-1))          # MVGenModel.py:53-56
+            pano.set_timesteps(timestep[:, 0])                # MVGenModel.py:53,59-60
+            pers.set_text(prompt_embd.flatten(0, 1), text_key)
+        else:
+            pano.set_timesteps(timestep)
+        pano.set_text(pano_prompt_embd.flatten(0, 1), pano_text_key)
+
+        # conv_in (MVGenModel.py:85-91)
+        h = pers.conv_in(latents.flatten(0, 1)) if has_pers else None
+        p = pano.conv_in(pano_latent.flatten(0, 1))
+        skips, pano_skips = ([h] if has_pers else []), [p]
+
+        # encoder (MVGenModel.py:98-152)
+        for i, pblk in enumerate(pano.p.down):
+            for j, pres in enumerate(pblk["resnets"]):
+                if has_pers:
+                    blk = pers.p.down[i]
+                    h = pers.resnet(h, blk["resnets"][j])
+                    if blk["attns"] is not None:
+                        h = pers.transformer(h, blk["attns"][j])
+                    skips.append(h)
+                p = pano.resnet(p, pres)
+                if pblk["attns"] is not None:
+                    p = pano.transformer(p, pblk["attns"][j])
+                pano_skips.append(p)
+            if pblk["down"] is not None:
+                for j, pd in enumerate(pblk["down"]):
+                    if has_pers:
+                        h = pers.downsample(h, pers.p.down[i]["down"][j])
+                    p = pano.downsample(p, pd)
+                if has_pers:
+                    skips.append(h)
+                pano_skips.append(p)  # skips are taken BEFORE the fusion (MVGenModel.py:146-152)
+                if has_pers:
+                    h, p = self.cp_blocks_encoder[i].forward_tokens(h, p, cam_key, par)
+
+        # mid (MVGenModel.py:172-207)
+        if has_pers:
+            h = pers.resnet(h, pers.p.mid["resnets"][0])
+        p = pano.resnet(p, pano.p.mid["resnets"][0])
+        for i, pat in enumerate(pano.p.mid["attns"]):
+            if has_pers:
+                h = pers.transformer(h, pers.p.mid["attns"][i])
+                h = pers.resnet(h, pers.p.mid["resnets"][i + 1])
+            p = pano.transformer(p, pat)
+            p = pano.resnet(p, pano.p.mid["resnets"][i + 1])
+        if has_pers:
+            h, p = self.cp_blocks_mid.forward_tokens(h, p, cam_key, par)
+
+        # decoder (MVGenModel.py:210-277)
+        for i, pblk in enumerate(pano.p.up):
+            for j, pres in enumerate(pblk["resnets"]):
+                if has_pers:
+                    blk = pers.p.up[i]
+                    h = pers.resnet(pers.concat(h, skips.pop()), blk["resnets"][j])
+                    if blk["attns"] is not None:
+                        h = pers.transformer(h, blk["attns"][j])
+                p = pano.resnet(pano.concat(p, pano_skips.pop()), pres)
+                if pblk["attns"] is not None:
+                    p = pano.transformer(p, pblk["attns"][j])
+            if pblk["up"] is not None:
+                if has_pers:
+                    h, p = self.cp_blocks_decoder[i].forward_tokens(h, p, cam_key, par)  # fusion BEFORE the upsampler
+                for j, pu in enumerate(pblk["up"]):
+                    if has_pers:
+                        h = pers.upsample(h, pers.p.up[i]["up"][j])
+                    p = pano.upsample(p, pu)
+
+        # heads (MVGenModel.py:279-297)
+        sample = None
+        if has_pers:
+            s = pers.conv_out(h)
+            sample = s.reshape(b, m, *s.shape[1:]).to(latents.dtype)
+        ps = pano.conv_out(p)[:, None]
+        if par is not None:
+            sample, ps = par.gather_outputs(sample, ps, b_full, m_full)
+        return sample, ps.to(pano_latent.dtype)

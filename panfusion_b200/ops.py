@@ -11,6 +11,15 @@ from . import _lib
 from ._lib import PF_ACT_GEGLU, PF_ACT_GELU, PF_ACT_NONE, PF_ACT_SILU, FmhaArgs, GemmArgs  # noqa: F401
 
 
+# number of CUDA kernels launched through this module (bench.py reports it as `gpu_launches`)
+LAUNCHES = 0
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _vp(t: Optional[Tensor]):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -58,6 +67,7 @@ def gemm_taps(A: Tensor, B: Tensor, out: Tensor, *, M: int, Kc: int, taps: Seque
     if image_map is not None:
         a.map_mode = 1
         a.Hm, a.Wm, a.i0, a.j0, a.Hout, a.Wout = (int(v) for v in image_map)
+    _count(1)
     _lib.check(_lib.lib().pf_gemm_taps(C.byref(a), _st()))
     return out
 
@@ -89,5 +99,158 @@ def fmha(q: Tensor, k: Tensor, v: Tensor, out: Tensor, *, heads: int, head_dim: 
             a.bias_bstride, a.bias_ld = (bias.stride(0) if bias.shape[0] > 1 else 0), bias.stride(1)
         else:
             a.bias_bstride, a.bias_ld = 0, bias.stride(0)
+    _count(1)
     _lib.check(_lib.lib().pf_fmha_fwd(C.byref(a), _st()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation / preparation
+# ------------------------------------------------------------------------------------------------
+def groupnorm_stats(x: Tensor, N: int, H: int, W: int, groups: int, eps: float, circ: int = 0) -> Tensor:
+    """x: [N*H*W, C] tokens -> mean_rstd [N, groups, 2] fp32 (statistics over the circularly extended image)."""
+    Cc = x.shape[1]
+    lib = _lib.lib()
+    ws = torch.empty(lib.pf_groupnorm_ws_floats(N, groups), dtype=torch.float32, device=x.device)
+    out = torch.empty((N, groups, 2), dtype=torch.float32, device=x.device)
+    _count(2)
+    _lib.check(lib.pf_groupnorm_stats(_vp(x), _lib.dtype_code(x.dtype), N, H, W, Cc, x.stride(0), groups, circ,
+                                      _f(eps), _vp(ws), _vp(out), _st()))
+    return out
+
+
+def _f(v: float):
+    return C.c_float(float(v))
+
+
+def conv_prep(x: Tensor, N: int, H: int, W: int, *, stats: Optional[Tensor] = None, gamma: Optional[Tensor] = None,
+              beta: Optional[Tensor] = None, groups: int = 32, act: int = PF_ACT_NONE, circ: int = 0, up: int = 1,
+              phases: int = 1, halo: int = 1) -> Tensor:
+    """-> [phases * N * Ho * Wo, C] tap-GEMM A operand (see pf_conv_prep)."""
+    Cc = x.shape[1]
+    Hu, Wu = H * up, (W + 2 * circ) * up
+    if phases == 4:
+        Ho, Wo = Hu // 2 + 1, Wu // 2 + 1
+    else:
+        Ho, Wo = Hu + 2 * halo, Wu + 2 * halo
+    out = torch.empty((phases * N * Ho * Wo, Cc), dtype=x.dtype, device=x.device)
+    _count(1)
+    _lib.check(_lib.lib().pf_conv_prep(_vp(x), _vp(out), _lib.dtype_code(x.dtype), N, H, W, Cc, x.stride(0),
+                                       _vp(stats), _vp(gamma), _vp(beta), groups, act, circ, up, phases, halo, _st()))
+    return out
+
+
+def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, pe: Optional[Tensor] = None) -> Tensor:
+    T, Cc = x.shape
+    out = torch.empty((T, Cc), dtype=x.dtype, device=x.device)
+    pe_rows = pe.shape[0] if pe is not None else 0
+    if pe is not None:
+        assert pe.dtype == torch.float32 and pe.is_contiguous() and pe.shape[1] == Cc and T % pe_rows == 0
+    _count(1)
+    _lib.check(_lib.lib().pf_layernorm(_vp(x), x.stride(0), _vp(out), out.stride(0), _lib.dtype_code(x.dtype), T, Cc,
+                                       _vp(pe), pe_rows, _vp(gamma), _vp(beta), _f(eps), _st()))
+    return out
+
+
+def conv_in(x: Tensor, w: Tensor, b: Optional[Tensor], dtype: torch.dtype, circ: bool) -> Tensor:
+    """x NCHW fp32 -> tokens [N*H*W, Cout]."""
+    N, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    out = torch.empty((N * H * W, Cout), dtype=dtype, device=x.device)
+    _count(1)
+    _lib.check(_lib.lib().pf_conv_in(_vp(x), _vp(w), _vp(b), _vp(out), _lib.dtype_code(dtype), N, Cin, H, W, Cout,
+                                     int(circ), _st()))
+    return out
+
+
+def conv_out(x: Tensor, N: int, H: int, W: int, stats: Tensor, gamma: Tensor, beta: Tensor, groups: int, w: Tensor,
+             b: Optional[Tensor], circ: bool) -> Tensor:
+    """tokens -> GroupNorm -> SiLU -> 3x3 conv -> NCHW fp32 [N, Cout, H, W]."""
+    Cc, Cout = x.shape[1], w.shape[0]
+    out = torch.empty((N, Cout, H, W), dtype=torch.float32, device=x.device)
+    _count(1)
+    _lib.check(_lib.lib().pf_conv_out(_vp(x), x.stride(0), _lib.dtype_code(x.dtype), _vp(stats), _vp(gamma), _vp(beta),
+                                      groups, _vp(w), _vp(b), _vp(out), N, H, W, Cc, Cout, int(circ), _st()))
+    return out
+
+
+def copy2d(src: Tensor, dst: Tensor) -> None:
+    """dst[:, :cols] = src (row-strided 16-bit 2-D copy); src/dst may be column slices."""
+    rows, cols = src.shape
+    assert dst.shape == src.shape and src.stride(1) == 1 and dst.stride(1) == 1
+    _count(1)
+    _lib.check(_lib.lib().pf_copy2d(_vp(src), src.stride(0), _vp(dst), dst.stride(0), C.c_longlong(rows), cols, _st()))
+
+
+def timestep_embed(t: Tensor, dim: int, dtype: torch.dtype) -> Tensor:
+    n = t.numel()
+    out = torch.empty((n, dim), dtype=dtype, device=t.device)
+    _count(1)
+    _lib.check(_lib.lib().pf_timestep_embed(_vp(t), _vp(out), _lib.dtype_code(dtype), n, dim, _st()))
+    return out
+
+
+def cfg_ddim_step(x: Tensor, eps: Tensor, out: Tensor, guidance: float, alpha_t: float, alpha_prev: float,
+                  roll: int = 0) -> Tensor:
+    """x, out fp32 [..., W]; eps fp32 with 2x the elements of x ([uncond; text])."""
+    assert x.dtype == eps.dtype == out.dtype == torch.float32 and x.is_contiguous() and eps.is_contiguous()
+    assert eps.numel() == 2 * x.numel() and out.is_contiguous() and out.numel() == x.numel()
+    _count(1)
+    _lib.check(_lib.lib().pf_cfg_ddim_step(_vp(x), _vp(eps), _vp(out), C.c_longlong(x.numel()), x.shape[-1], int(roll),
+                                           _f(guidance), _f(alpha_t), _f(alpha_prev), _st()))
+    return out
+
+
+def cfg_ddim_step_dev(x: Tensor, eps: Tensor, out: Tensor, guidance: float, coef: Tensor, roll: int = 0) -> Tensor:
+    """Same as cfg_ddim_step with (c_x, c_eps) in a 2-float device tensor (graph-replayable)."""
+    assert x.dtype == eps.dtype == out.dtype == coef.dtype == torch.float32
+    assert x.is_contiguous() and eps.is_contiguous() and out.is_contiguous() and eps.numel() == 2 * x.numel()
+    _count(1)
+    _lib.check(_lib.lib().pf_cfg_ddim_step_dev(_vp(x), _vp(eps), _vp(out), C.c_longlong(x.numel()), x.shape[-1],
+                                               int(roll), _f(guidance), _vp(coef), _st()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# EPPA tables
+# ------------------------------------------------------------------------------------------------
+_BLUR5 = None
+
+
+def _blur5():
+    """5 taps of kornia's sigma-1 gaussian, computed like kornia does (fp32 torch ops), as a ctypes float[5]."""
+    global _BLUR5
+    if _BLUR5 is None:
+        x = torch.arange(5, dtype=torch.float32) - 2
+        g = torch.exp(-x.pow(2.0) / 2.0)
+        g = g / g.sum()
+        _BLUR5 = (C.c_float * 5)(*g.tolist())
+    return _BLUR5
+
+
+def eppa_tables(cams_e2p: Tensor, cams_p2e: Tensor, m: int, ph: int, pw: int, eh: int, ew: int):
+    """cams_*: [V, 20] float64 device records -> (bias1 [V/m, E, m*P], bias2 [V/m, m*P, E]) fp32."""
+    V = cams_e2p.shape[0]
+    P, E = ph * pw, eh * ew
+    dev = cams_e2p.device
+    ws_idx = torch.empty(4 * V * (P + E), dtype=torch.int32, device=dev)
+    ws_w = torch.empty(4 * V * (P + E), dtype=torch.float32, device=dev)
+    bias1 = torch.empty((V // m, E, m * P), dtype=torch.float32, device=dev)
+    bias2 = torch.empty((V // m, m * P, E), dtype=torch.float32, device=dev)
+    _count(3)
+    _lib.check(_lib.lib().pf_eppa_tables(_vp(cams_e2p), _vp(cams_p2e), V, m, ph, pw, eh, ew, _blur5(), _vp(ws_idx),
+                                         _vp(ws_w), _vp(bias1), _vp(bias2), _st()))
+    return bias1, bias2
+
+
+def eppa_pe(cams_e2p: Tensor, ph: int, pw: int, eh: int, ew: int, freq_bands: Tensor):
+    """-> (pers_pe [V*P, 4N], equi_pe [E, 4N]) fp32 SphericalPE tables."""
+    V = cams_e2p.shape[0]
+    nf = freq_bands.numel()
+    dev = cams_e2p.device
+    pers_pe = torch.empty((V * ph * pw, 4 * nf), dtype=torch.float32, device=dev)
+    equi_pe = torch.empty((eh * ew, 4 * nf), dtype=torch.float32, device=dev)
+    fb = freq_bands.to(device=dev, dtype=torch.float32).contiguous()
+    _count(1)
+    _lib.check(_lib.lib().pf_eppa_pe(_vp(cams_e2p), V, ph, pw, eh, ew, _vp(fb), nf, _vp(pers_pe), _vp(equi_pe), _st()))
+    return pers_pe, equi_pe

@@ -1,0 +1,90 @@
+"""Sharding of one denoise step over the GPUs of a node: one process per GPU, `torch.distributed` for plumbing.
+
+The reference has no model parallelism (Lightning DDP over prompts only, main.py:63; `predict` uses no collective).
+What shards naturally: the two classifier-free-guidance halves are independent until the CFG combine
+(PanoGenerator.py:253-262), and perspective views are independent everywhere except inside EPPA, where the panorama
+queries attend to the keys/values of ALL views (models/pano/modules.py:44-48). Layout used here:
+
+    world = batch_shards x view_shards,   rank -> (bs, vs) = divmod(rank, view_shards)
+    rank owns CFG/batch elements [bs*b/B .. ) and views [vs*m/V .. ); the panorama branch runs once per batch shard
+    (replicated over the view shards of that batch shard).
+
+Collectives: (1) per EPPA block, ONE all-gather of the projected K|V of the local views inside the batch shard's
+view group (skipped when view_shards == 1, e.g. N = 2 = pure CFG split); (2) per forward, one all-gather of the tiny
+eps outputs over the world so every rank ends the step with identical full latents.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def pick_layout(world: int, b: int, m: int) -> tuple[int, int]:
+    """(batch_shards, view_shards): split the CFG batch first (halves the panorama branch per rank), views next."""
+    batch_shards = 2 if (world % 2 == 0 and b % 2 == 0) else 1
+    view_shards = world // batch_shards
+    if b % batch_shards or m % view_shards:
+        raise ValueError(f"cannot shard b={b} x m={m} over {world} ranks as {batch_shards} x {view_shards}")
+    return batch_shards, view_shards
+
+
+class ViewParallel:
+    def __init__(self, group=None, batch_shards: Optional[int] = None, view_shards: Optional[int] = None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.batch_shards, self.view_shards = batch_shards, view_shards
+        self._view_groups = None
+
+    def configure(self, b: int, m: int) -> None:
+        if self.batch_shards is None or self.view_shards is None:
+            self.batch_shards, self.view_shards = pick_layout(self.world, b, m)
+        if self.batch_shards * self.view_shards != self.world:
+            raise ValueError("batch_shards * view_shards must equal the world size")
+        if self._view_groups is None:
+            # every rank must create every subgroup, in the same order
+            self._view_groups = []
+            for bs in range(self.batch_shards):
+                ranks = [bs * self.view_shards + v for v in range(self.view_shards)]
+                self._view_groups.append(dist.new_group(ranks) if self.view_shards > 1 else None)
+        self.bs, self.vs = divmod(self.rank, self.view_shards)
+
+    @property
+    def view_group(self):
+        return self._view_groups[self.bs]
+
+    def slices(self, b: int, m: int) -> tuple[slice, slice]:
+        bl, ml = b // self.batch_shards, m // self.view_shards
+        return slice(self.bs * bl, (self.bs + 1) * bl), slice(self.vs * ml, (self.vs + 1) * ml)
+
+    def gather_views(self, x: Tensor) -> Tensor:
+        """x: [b_loc, L_loc, C] contiguous -> [b_loc, view_shards * L_loc, C] in view order."""
+        if self.view_shards == 1:
+            return x
+        bl, L, C = x.shape
+        out = torch.empty((self.view_shards * bl, L, C), dtype=x.dtype, device=x.device)  # concat along dim 0
+        dist.all_gather_into_tensor(out, x.contiguous(), group=self.view_group)
+        out = out.reshape(self.view_shards, bl, L, C)
+        if bl == 1:
+            return out.reshape(1, self.view_shards * L, C)
+        return out.permute(1, 0, 2, 3).reshape(bl, self.view_shards * L, C)
+
+    def gather_outputs(self, sample_loc: Optional[Tensor], pano_loc: Tensor, b: int, m: int):
+        """sample_loc [b_loc, m_loc, ...], pano_loc [b_loc, 1, ...] -> full [b, m, ...], [b, 1, ...] on every rank."""
+        bl, ml = b // self.batch_shards, m // self.view_shards
+        pano_all = torch.empty((self.world * pano_loc.shape[0], *pano_loc.shape[1:]), dtype=pano_loc.dtype,
+                               device=pano_loc.device)
+        dist.all_gather_into_tensor(pano_all, pano_loc.contiguous(), group=self.group)
+        pano = pano_all.reshape(self.batch_shards, self.view_shards, *pano_loc.shape)[:, 0].reshape(b, *pano_loc.shape[1:])
+        sample = None
+        if sample_loc is not None:
+            s_all = torch.empty((self.world * sample_loc.shape[0], *sample_loc.shape[1:]), dtype=sample_loc.dtype,
+                                device=sample_loc.device)
+            dist.all_gather_into_tensor(s_all, sample_loc.contiguous(), group=self.group)
+            tail = sample_loc.shape[2:]
+            s = s_all.reshape(self.batch_shards, self.view_shards, bl, ml, *tail)
+            sample = s.permute(0, 2, 1, 3, *range(4, 4 + len(tail))).reshape(b, m, *tail)
+        return sample, pano

@@ -1,0 +1,195 @@
+"""The sampling loop around the denoiser behind the reference's method names.
+
+Reference: models/pano/PanFusion.py:30-43 (init_noise), :100-112 (forward_cls_free), :114-123 (rotate_latent),
+:146-164 (the 50-step loop), models/pano/PanoGenerator.py:240-269 (CFG pair / combine, latent roll) and diffusers
+DDIMScheduler [3P] (SD-2 config). Per step the reference runs: torch.roll + theta += 90, torch.cat x2 of every
+input, the denoiser, the CFG combine, two scheduler.step calls. Here the combine, both DDIM updates and the NEXT
+step's roll are one tiny kernel per latent (pf_cfg_ddim_step_dev), the view noise is the e2p-nearest kernel, and
+— because every shape is static and all camera-dependent tables are cached — the whole step is captured once per
+rotation phase into a CUDA graph and replayed.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import geometry, ops
+
+
+class DDIMSchedule:
+    """Coefficients of diffusers DDIMScheduler for the SD-2 config (scaled_linear betas, steps_offset 1, epsilon
+    prediction, eta 0, set_alpha_to_one False, 'leading' spacing) [3P]."""
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, steps_offset=1):
+        betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.final_alpha_cumprod = self.alphas_cumprod[0]
+        self.num_train_timesteps, self.steps_offset = num_train_timesteps, steps_offset
+        self.timesteps: Optional[Tensor] = None
+        self.num_inference_steps = 0
+
+    def set_timesteps(self, n: int) -> None:
+        self.num_inference_steps = n
+        ratio = self.num_train_timesteps // n
+        self.timesteps = torch.from_numpy((np.arange(0, n) * ratio).round()[::-1].copy().astype(np.int64)
+                                          + self.steps_offset)
+
+    def alphas(self, t: int) -> tuple[float, float]:
+        prev_t = t - self.num_train_timesteps // self.num_inference_steps
+        a_t = float(self.alphas_cumprod[t])
+        a_prev = float(self.alphas_cumprod[prev_t]) if prev_t >= 0 else float(self.final_alpha_cumprod)
+        return a_t, a_prev
+
+    def coefficients(self, t: int) -> tuple[float, float]:
+        """x_prev = c_x * x + c_eps * eps."""
+        a_t, a_prev = self.alphas(t)
+        sa = math.sqrt(a_prev / a_t)
+        return sa, math.sqrt(1.0 - a_prev) - sa * math.sqrt(1.0 - a_t)
+
+
+class PanFusionSampler:
+    def __init__(self, mv_base_model, guidance_scale: float = 9.0, diff_timestep: int = 50, rot_diff: float = 90.0,
+                 use_cuda_graph: bool = True):
+        self.mv_base_model = mv_base_model
+        self.guidance_scale, self.diff_timestep, self.rot_diff = guidance_scale, diff_timestep, rot_diff
+        self.scheduler = DDIMSchedule()
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
+        self._pool = None
+        self.launches_per_step = None
+
+    # ---- PanFusion.py:30-43 -------------------------------------------------------------------------
+    def init_noise(self, bs, equi_h, equi_w, pers_h, pers_w, cameras, device, generator=None):
+        cams = {k: v.flatten(0, 1) for k, v in cameras.items()}
+        m = len(cams["FoV"]) // bs
+        pano_noise = torch.randn(bs, 1, 4, equi_h, equi_w, device=device, generator=generator)
+        rep = pano_noise.expand(-1, m, -1, -1, -1).flatten(0, 1).contiguous()
+        noise = geometry.e2p(rep, cams["FoV"], cams["theta"], cams["phi"], (pers_h, pers_w), mode="nearest")
+        return pano_noise, noise.reshape(bs, m, *noise.shape[1:])
+
+    # ---- PanFusion.py:114-123 / PanoGenerator.py:264-269 ------------------------------------------
+    def rotate_latent(self, pano_latent, cameras, degree=None):
+        degree = self.rot_diff if degree is None else degree
+        if degree % 360 == 0:
+            return pano_latent, cameras
+        pano_latent = torch.roll(pano_latent, int(degree / 360 * pano_latent.shape[-1]), dims=-1)
+        cameras = dict(cameras)
+        cameras["theta"] = (cameras["theta"] + degree) % 360
+        return pano_latent, cameras
+
+    # ---- PanFusion.py:100-112 -----------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_cls_free(self, latents, pano_latent, timestep, prompt_embd, pano_prompt_embd, cameras):
+        dup = lambda t: torch.cat([t] * 2)
+        cams2 = {k: dup(v) for k, v in cameras.items()}
+        eps, pano_eps = self.mv_base_model(dup(latents), dup(pano_latent), dup(timestep), prompt_embd,
+                                           pano_prompt_embd, cams2)
+        comb = lambda e: e[:e.shape[0] // 2] + self.guidance_scale * (e[e.shape[0] // 2:] - e[:e.shape[0] // 2])
+        return comb(eps), comb(pano_eps)
+
+    # ---- one iteration of PanFusion.py:146-162 on static buffers ------------------------------------
+    def _step_body(self, st, cameras):
+        """st: dict of static device tensors. The pano latent in st is ALREADY rotated for this step; the DDIM
+        kernel writes the next step's latent pre-rotated by rot_diff."""
+        dup = lambda t: torch.cat([t] * 2)
+        cams2 = {k: dup(v) for k, v in cameras.items()}
+        eps, pano_eps = self.mv_base_model(dup(st["latents"]), dup(st["pano"]), dup(st["timestep"]), st["prompt"],
+                                           st["pano_prompt"], cams2)
+        ops.cfg_ddim_step_dev(st["latents"], eps.contiguous(), st["latents_next"], self.guidance_scale, st["coef"])
+        W = st["pano"].shape[-1]
+        ops.cfg_ddim_step_dev(st["pano"], pano_eps.contiguous(), st["pano_next"], self.guidance_scale, st["coef"],
+                              roll=int(self.rot_diff / 360 * W) % W)
+        st["latents"].copy_(st["latents_next"])
+        st["pano"].copy_(st["pano_next"])
+
+    # ---- the hot loop (PanFusion.py:146-164) as start / step / finish ---------------------------------
+    @torch.no_grad()
+    def start(self, latents: Tensor, pano_latent: Tensor, prompt_embd: Tensor, pano_prompt_embd: Tensor,
+              cameras: dict) -> None:
+        """Bind static buffers. prompt_embd [2, m, 77, C] / pano_prompt_embd [2, 1, 77, C] are the CFG concatenations
+        [null; text] (PanFusion.py:135-138); cameras: dict of tensors [1, m] (CPU or CUDA)."""
+        dev = latents.device
+        self.scheduler.set_timesteps(self.diff_timestep)
+        m = latents.shape[1]
+        W = pano_latent.shape[-1]
+        self._roll = int(self.rot_diff / 360 * W) if self.rot_diff % 360 else 0
+        coefs = torch.tensor([self.scheduler.coefficients(int(t)) for t in self.scheduler.timesteps],
+                             dtype=torch.float32)
+        st = dict(latents=latents.to(torch.float32).contiguous().clone(),
+                  # the rotation of the first step (PanFusion.py:149); later ones are fused into the DDIM kernel
+                  pano=torch.roll(pano_latent.to(torch.float32), self._roll, dims=-1).contiguous(),
+                  timestep=torch.zeros((1, m), dtype=torch.float32, device=dev),
+                  prompt=prompt_embd.contiguous(), pano_prompt=pano_prompt_embd.contiguous(),
+                  coef=torch.zeros(2, dtype=torch.float32, device=dev),
+                  coef_table=coefs.to(dev), ts_table=self.scheduler.timesteps.to(dev, torch.float32))
+        st["latents_next"], st["pano_next"] = torch.empty_like(st["latents"]), torch.empty_like(st["pano"])
+        self._st = st
+        self._cameras = {k: v.detach().to("cpu", torch.float32) for k, v in cameras.items()}
+        self._curr_rot = 0.0
+        self._graphs = {}
+
+    @torch.no_grad()
+    def step(self, i: int) -> None:
+        """Iteration i of the loop: rotate (cameras here, latent already rotated), CFG forward, DDIM updates."""
+        st = self._st
+        self._curr_rot += self.rot_diff
+        if self.rot_diff % 360:
+            self._cameras = dict(self._cameras)
+            self._cameras["theta"] = (self._cameras["theta"] + self.rot_diff) % 360
+        st["timestep"].copy_(st["ts_table"][i].expand_as(st["timestep"]))
+        st["coef"].copy_(st["coef_table"][i])
+        self._run_step(st, self._cameras)
+
+    @torch.no_grad()
+    def finish(self, rotate_back: bool = True):
+        """-> (latents, pano_latent). rotate_back applies PanFusion.py:164 (roll by -sum of rotations); without it the
+        panorama is returned in the last step's rotated frame (what the loop variable holds in the reference)."""
+        st = self._st
+        W = st["pano"].shape[-1]
+        shift = -self._roll  # the DDIM kernel pre-rotated for a step that never ran
+        if rotate_back and self.rot_diff % 360:
+            shift += int(-self._curr_rot / 360 * W)
+        return st["latents"].clone(), torch.roll(st["pano"], shift % W, dims=-1)
+
+    @torch.no_grad()
+    def denoise(self, latents, pano_latent, prompt_embd, pano_prompt_embd, cameras, num_steps=None, start_step=0,
+                rotate_back=True):
+        self.start(latents, pano_latent, prompt_embd, pano_prompt_embd, cameras)
+        for i in range(start_step, start_step + (num_steps or self.diff_timestep)):
+            self.step(i)
+        lat, pano = self.finish(rotate_back)
+        return lat.to(latents.dtype), pano.to(pano_latent.dtype)
+
+    def _run_step(self, st, cameras):
+        if not self.use_cuda_graph:
+            l0 = ops.LAUNCHES
+            self._step_body(st, cameras)
+            self.launches_per_step = ops.LAUNCHES - l0
+            return
+        key = (tuple(cameras["theta"].reshape(-1).tolist()), tuple(cameras["phi"].reshape(-1).tolist()),
+               tuple(cameras["FoV"].reshape(-1).tolist()), tuple(st["latents"].shape), tuple(st["pano"].shape),
+               st["latents"].data_ptr(), st["pano"].data_ptr(), st["prompt"].data_ptr())
+        entry = self._graphs.get(key)
+        if entry is None:
+            # eager warm-up builds the camera tables / packs weights / sets kernel attributes, then capture
+            snap = {k: st[k].clone() for k in ("latents", "pano")}
+            self._step_body(st, cameras)
+            torch.cuda.synchronize()
+            st["latents"].copy_(snap["latents"])
+            st["pano"].copy_(snap["pano"])
+            g = torch.cuda.CUDAGraph()
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            l0 = ops.LAUNCHES
+            with torch.cuda.graph(g, pool=self._pool):
+                self._step_body(st, cameras)
+            self.launches_per_step = ops.LAUNCHES - l0  # kernels of ours inside one replayed step
+            self._graphs[key] = g
+            st["latents"].copy_(snap["latents"])
+            st["pano"].copy_(snap["pano"])
+            entry = g
+        entry.replay()
