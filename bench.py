@@ -159,6 +159,18 @@ def run_b200(args):
 
     n_sched = sampler.diff_timestep
     sampler.start(lat, pano, prompt, pano_prompt, inp["cams"])
+    if args.profile_one_step:
+        # ncu --profile-from-start off: tables/weights warmed by 4 eager steps, then exactly one step is profiled
+        sampler.use_cuda_graph = False
+        for i in range(4):
+            sampler.step(i)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        sampler.step(4)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled_step_launches": sampler.launches_per_step}))
+        return
     # preparation (untimed, not counted as warm-up): build camera tables + capture one CUDA graph per rotation phase
     phases = 4 if sampler.rot_diff % 360 else 1
     l0 = ops.LAUNCHES
@@ -393,6 +405,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-micro", action="store_true", help="skip the isolated kernel rooflines")
     ap.add_argument("--cpu-budget", type=float, default=30.0)
+    ap.add_argument("--profile-one-step", action="store_true", help="for ncu --profile-from-start off: profile one eager step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -127,9 +127,19 @@ typedef struct pf_fmha_args {
   const float* bias;
   int64_t bias_bstride;
   int32_t bias_ld;
+  /* optional block-sparsity hint for the bias: flags[b][ceil(Lq/128)][ceil(Lk/64)] bytes, non-zero = every entry of
+   * that 128x64 bias tile is exactly -1 (no geometric correspondence, SURVEY.md A.4: ~85% of the EPPA tiles), so the
+   * kernel substitutes the constant instead of reading the tile. NULL = read everything. Build with
+   * pf_bias_tile_flags. */
+  const uint8_t* bias_flags;
+  int64_t flags_bstride;
+  int32_t flags_ld;
 } pf_fmha_args;
 
 int pf_fmha_fwd(const pf_fmha_args* args, void* stream);
+/* flags[g][qt][kt] = 1 iff bias[g][qt*128 .. , kt*64 ..] is entirely == -1.0f (tiles clipped at Lq / Lk) */
+int pf_bias_tile_flags(const float* bias, int G, int Lq, int Lk, int bias_ld, int64_t bias_bstride, uint8_t* flags,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm statistics of a channels-last image x[N, H, W, C] (row stride ld), computed over the image

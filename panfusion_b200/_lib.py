@@ -46,6 +46,7 @@ class FmhaArgs(C.Structure):
         ("q_ld", C.c_int32), ("k_ld", C.c_int32), ("v_ld", C.c_int32), ("out_ld", C.c_int32),
         ("q_bstride", C.c_int64), ("k_bstride", C.c_int64), ("v_bstride", C.c_int64),
         ("scale", C.c_float), ("bias", C.c_void_p), ("bias_bstride", C.c_int64), ("bias_ld", C.c_int32),
+        ("bias_flags", C.c_void_p), ("flags_bstride", C.c_int64), ("flags_ld", C.c_int32),
     ]
 
 
@@ -73,7 +74,7 @@ EXPORTS = [
     "pf_last_error", "pf_version", "pf_check_device",
     "pf_e2p", "pf_p2e",
     "pf_gemm_taps", "pf_gemm_pick_block_n",
-    "pf_fmha_fwd",
+    "pf_fmha_fwd", "pf_bias_tile_flags",
     "pf_groupnorm_ws_floats", "pf_groupnorm_stats", "pf_conv_prep", "pf_layernorm",
     "pf_conv_in", "pf_conv_out", "pf_copy2d", "pf_timestep_embed", "pf_cfg_ddim_step", "pf_cfg_ddim_step_dev",
     "pf_eppa_tables", "pf_eppa_pe",

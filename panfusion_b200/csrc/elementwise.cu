@@ -13,38 +13,54 @@ template <bool BF16>
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                uint16_t* __restrict__ out, int N, int Cin, int H, int W, int Cout, int circ) {
+  // weights transposed into shared memory as [Cin*9][Cout] (+bias row): lanes read consecutive output channels
+  extern __shared__ float s_w[];
+  const int K = Cin * 9;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+    const int co = i % Cout, k = i / Cout;  // k = ci*9 + tap
+    s_w[i] = w[(size_t)co * K + k];
+  }
+  float* s_b = s_w + K * Cout;
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
   const int vecs = Cout / 8;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)N * H * W * vecs) return;
-  const int v = int(idx % vecs);
-  const long long pix = idx / vecs;
-  const int xx = int(pix % W), yy = int((pix / W) % H), n = int(pix / ((long long)W * H));
-  float acc[8];
+  const long long total = (long long)N * H * W * vecs;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = int(idx % vecs);
+    const long long pix = idx / vecs;
+    const int xx = int(pix % W), yy = int((pix / W) % H), n = int(pix / ((long long)W * H));
+    float acc[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = bias ? __ldg(bias + v * 8 + e) : 0.f;
-  for (int ci = 0; ci < Cin; ++ci) {
-    const float* xp = x + ((size_t)n * Cin + ci) * H * W;
+    for (int e = 0; e < 8; ++e) acc[e] = s_b[v * 8 + e];
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float* xp = x + ((size_t)n * Cin + ci) * H * W;
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int sy = yy + dy - 1;
-      if (sy < 0 || sy >= H) continue;
+      for (int dy = 0; dy < 3; ++dy) {
+        const int sy = yy + dy - 1;
+        if (sy < 0 || sy >= H) continue;
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        int sx = xx + dx - 1;
-        if (circ) {
-          sx = sx < 0 ? sx + W : (sx >= W ? sx - W : sx);
-        } else if (sx < 0 || sx >= W) {
-          continue;
+        for (int dx = 0; dx < 3; ++dx) {
+          int sx = xx + dx - 1;
+          if (circ) {
+            sx = sx < 0 ? sx + W : (sx >= W ? sx - W : sx);
+          } else if (sx < 0 || sx >= W) {
+            continue;
+          }
+          const float val = __ldg(xp + sy * W + sx);
+          const float4* wr = reinterpret_cast<const float4*>(s_w + (size_t)(ci * 9 + dy * 3 + dx) * Cout + v * 8);
+          const float4 w0 = wr[0], w1 = wr[1];
+          acc[0] = fmaf(val, w0.x, acc[0]); acc[1] = fmaf(val, w0.y, acc[1]);
+          acc[2] = fmaf(val, w0.z, acc[2]); acc[3] = fmaf(val, w0.w, acc[3]);
+          acc[4] = fmaf(val, w1.x, acc[4]); acc[5] = fmaf(val, w1.y, acc[5]);
+          acc[6] = fmaf(val, w1.z, acc[6]); acc[7] = fmaf(val, w1.w, acc[7]);
         }
-        const float val = __ldg(xp + sy * W + sx);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(val, __ldg(w + (((size_t)(v * 8 + e) * Cin + ci) * 3 + dy) * 3 + dx), acc[e]);
       }
     }
+    *reinterpret_cast<uint4*>(out + (size_t)pix * Cout + v * 8) =
+        make_uint4(pack2<BF16>(acc[0], acc[1]), pack2<BF16>(acc[2], acc[3]), pack2<BF16>(acc[4], acc[5]),
+                   pack2<BF16>(acc[6], acc[7]));
   }
-  *reinterpret_cast<uint4*>(out + (size_t)pix * Cout + v * 8) =
-      make_uint4(pack2<BF16>(acc[0], acc[1]), pack2<BF16>(acc[2], acc[3]), pack2<BF16>(acc[4], acc[5]),
-                 pack2<BF16>(acc[6], acc[7]));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -170,12 +186,21 @@ extern "C" int pf_conv_in(const float* x, const float* w, const float* bias, voi
   PF_CHECK_ARG(dtype == PF_BF16 || dtype == PF_F16, "pf_conv_in: 16-bit output dtype required");
   PF_CHECK_ARG(N > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0 && Cout % 8 == 0, "pf_conv_in: bad shape");
   const long long total = (long long)N * H * W * (Cout / 8);
-  const unsigned blocks = (unsigned)((total + 255) / 256);
+  long long want = (total + 255) / 256;
+  const unsigned blocks = (unsigned)(want < 148 * 4 ? want : 148 * 4);  // persistent-ish: weights staged once per CTA
+  const size_t smem = ((size_t)Cin * 9 * Cout + Cout) * sizeof(float);
+  PF_CHECK_ARG(smem <= 200 * 1024, "pf_conv_in: Cin*9*Cout too large for shared memory");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == PF_BF16)
-    conv_in_kernel<true><<<blocks, 256, 0, st>>>(x, w, bias, static_cast<uint16_t*>(out), N, Cin, H, W, Cout, circ);
-  else
-    conv_in_kernel<false><<<blocks, 256, 0, st>>>(x, w, bias, static_cast<uint16_t*>(out), N, Cin, H, W, Cout, circ);
+  int rc;
+  if (dtype == PF_BF16) {
+    auto k = conv_in_kernel<true>;
+    if ((rc = check_cuda(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv_in attr"))) return rc;
+    k<<<blocks, 256, smem, st>>>(x, w, bias, static_cast<uint16_t*>(out), N, Cin, H, W, Cout, circ);
+  } else {
+    auto k = conv_in_kernel<false>;
+    if ((rc = check_cuda(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv_in attr"))) return rc;
+    k<<<blocks, 256, smem, st>>>(x, w, bias, static_cast<uint16_t*>(out), N, Cin, H, W, Cout, circ);
+  }
   PF_CHECK_LAUNCH("conv_in_kernel");
   return PF_OK;
 }

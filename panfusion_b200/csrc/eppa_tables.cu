@@ -221,7 +221,33 @@ eppa_pe_kernel(const double* __restrict__ cams_e2p, int V, int ph, int pw, int e
   dst[3 * nf + k] = cosf(at);
 }
 
+// flags[g][qt][kt] = 1 iff the 128 x 64 bias tile is entirely -1 (row of "no correspondence" entries)
+__global__ void __launch_bounds__(256)
+bias_tile_flags_kernel(const float* __restrict__ bias, int Lq, int Lk, int ld, long long bstride,
+                       uint8_t* __restrict__ flags) {
+  const int kt = blockIdx.x, qt = blockIdx.y, g = blockIdx.z;
+  const float* base = bias + (long long)g * bstride;
+  int ok = 1;
+  for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) {
+    const int r = qt * 128 + i / 64, c = kt * 64 + i % 64;
+    if (r < Lq && c < Lk && __ldg(base + (long long)r * ld + c) != -1.0f) ok = 0;
+  }
+  ok = __syncthreads_and(ok);
+  if (threadIdx.x == 0) flags[((size_t)g * gridDim.y + qt) * gridDim.x + kt] = (uint8_t)ok;
+}
+
 }  // namespace pf
+
+extern "C" int pf_bias_tile_flags(const float* bias, int G, int Lq, int Lk, int bias_ld, int64_t bias_bstride,
+                                  uint8_t* flags, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(bias && flags && G > 0 && Lq > 0 && Lk > 0 && bias_ld >= Lk, "pf_bias_tile_flags: bad arguments");
+  dim3 grid((Lk + 63) / 64, (Lq + 127) / 128, G);
+  PF_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "pf_bias_tile_flags: too many tiles");
+  bias_tile_flags_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(bias, Lq, Lk, bias_ld, bias_bstride, flags);
+  PF_CHECK_LAUNCH("bias_tile_flags_kernel");
+  return PF_OK;
+}
 
 extern "C" int pf_eppa_tables(const double* cams_e2p, const double* cams_p2e, int V, int m, int ph, int pw, int eh,
                               int ew, const float* blur5, int* ws_idx, float* ws_w, float* bias1, float* bias2,

@@ -28,7 +28,19 @@ struct FmhaParams {
   const float* bias;  // [bias_batches, Lq, bias_ld] or null
   long long bias_bstride;
   int bias_ld;
+  // optional: per (128-query x 64-key) tile flag, 1 = every bias entry of the tile equals -1 (no correspondence):
+  // the tile's loads are replaced by the constant. [bias_batches, ceil(Lq/128), ceil(Lk/64)] bytes.
+  const uint8_t* bias_flags;
+  long long flags_bstride;
+  int flags_ld;
 };
+
+// ex2.approx.ftz: one MUFU op (exp2f() adds denormal / range fix-up instructions we do not need: inputs are <= 0)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <int D>
 __host__ __device__ constexpr int fmha_smem_bytes() {
@@ -146,6 +158,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int row = quarter * 32 + lane;
     const int q = q0 + row;
     const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
+    constexpr float LOG2E = 1.4426950408889634f;
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
     float o_acc[D];
 #pragma unroll
@@ -155,8 +168,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int qq = q < p.Lq ? q : p.Lq - 1;
       bias_row = p.bias + (long long)b * p.bias_bstride + (long long)qq * p.bias_ld;
     }
-    constexpr float LOG2E = 1.4426950408889634f;
-
+    const uint8_t* flag_row = nullptr;
+    if constexpr (HAS_BIAS) {
+      if (p.bias_flags) flag_row = p.bias_flags + (long long)b * p.flags_bstride + (long long)qt * p.flags_ld;
+    }
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
@@ -167,28 +182,36 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld32(ts, raw);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) sv[e] = __uint_as_float(raw[e]) * p.scale_log2;
+        for (int e = 0; e < 32; ++e) sv[e] = __uint_as_float(raw[e]);
         tmem_ld32(ts + 32, raw);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) sv[32 + e] = __uint_as_float(raw[e]) * p.scale_log2;
+        for (int e = 0; e < 32; ++e) sv[32 + e] = __uint_as_float(raw[e]);
       }
       const int k0 = j * FA_BLOCK_N;
+      // sv <- logits in log2 units. Without bias the softmax scale is folded into the exp2 argument below (one FFMA
+      // per element); with bias: t = s*scale*log2e + bias*log2e.
       if constexpr (HAS_BIAS) {
-        if (k0 + FA_BLOCK_N <= p.Lk) {
+        const bool constant_tile = flag_row != nullptr && flag_row[j] != 0;
+        if (constant_tile) {
+#pragma unroll
+          for (int e = 0; e < FA_BLOCK_N; ++e) sv[e] = fmaf(sv[e], p.scale_log2, -LOG2E);
+        } else if (k0 + FA_BLOCK_N <= p.Lk) {
           const float4* b4 = reinterpret_cast<const float4*>(bias_row + k0);
 #pragma unroll
           for (int e = 0; e < FA_BLOCK_N / 4; ++e) {
             const float4 t = __ldg(b4 + e);
-            sv[4 * e + 0] = fmaf(t.x, LOG2E, sv[4 * e + 0]);
-            sv[4 * e + 1] = fmaf(t.y, LOG2E, sv[4 * e + 1]);
-            sv[4 * e + 2] = fmaf(t.z, LOG2E, sv[4 * e + 2]);
-            sv[4 * e + 3] = fmaf(t.w, LOG2E, sv[4 * e + 3]);
+            sv[4 * e + 0] = fmaf(t.x, LOG2E, sv[4 * e + 0] * p.scale_log2);
+            sv[4 * e + 1] = fmaf(t.y, LOG2E, sv[4 * e + 1] * p.scale_log2);
+            sv[4 * e + 2] = fmaf(t.z, LOG2E, sv[4 * e + 2] * p.scale_log2);
+            sv[4 * e + 3] = fmaf(t.w, LOG2E, sv[4 * e + 3] * p.scale_log2);
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < FA_BLOCK_N; ++e)
-            if (k0 + e < p.Lk) sv[e] = fmaf(__ldg(bias_row + k0 + e), LOG2E, sv[e]);
+          for (int e = 0; e < FA_BLOCK_N; ++e) {
+            const float bv = (k0 + e < p.Lk) ? __ldg(bias_row + k0 + e) : 0.f;
+            sv[e] = fmaf(bv, LOG2E, sv[e] * p.scale_log2);
+          }
         }
       }
       if (k0 + FA_BLOCK_N > p.Lk) {
@@ -196,20 +219,21 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int e = 0; e < FA_BLOCK_N; ++e)
           if (k0 + e >= p.Lk) sv[e] = -INFINITY;
       }
-      float mx = m_run;
+      // running max (raw logits when no bias: scale > 0 commutes with max)
+      float mx_raw = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < FA_BLOCK_N; ++e) mx = fmaxf(mx, sv[e]);
-      const float alpha = exp2f(m_run - mx);
+      for (int e = 0; e < FA_BLOCK_N; ++e) mx_raw = fmaxf(mx_raw, sv[e]);
+      const float sc = HAS_BIAS ? 1.0f : p.scale_log2;
+      const float mx = fmaxf(m_run, mx_raw * sc);
+      const float alpha = fast_exp2(m_run - mx);
       m_run = mx;
       float psum = 0.f;
       uint32_t pk[FA_BLOCK_N / 2];
 #pragma unroll
       for (int e = 0; e < FA_BLOCK_N; e += 2) {
-        const float p0 = exp2f(sv[e] - mx), p1 = exp2f(sv[e + 1] - mx);
-        // the row sum uses the rounded probabilities that the P V MMA consumes
+        const float p0 = fast_exp2(fmaf(sv[e], sc, -mx)), p1 = fast_exp2(fmaf(sv[e + 1], sc, -mx));
+        psum += p0 + p1;
         pk[e >> 1] = pack2<BF16>(p0, p1);
-        const float2 r = unpack2<BF16>(pk[e >> 1]);
-        psum += r.x + r.y;
       }
       l_run = l_run * alpha + psum;
 
@@ -294,6 +318,7 @@ static int launch_fmha(const pf_fmha_args* a, cudaStream_t st) {
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.out = a->out; p.out_ld = a->out_ld;
   p.bias = a->bias; p.bias_bstride = a->bias_bstride; p.bias_ld = a->bias_ld;
+  p.bias_flags = a->bias_flags; p.flags_bstride = a->flags_bstride; p.flags_ld = a->flags_ld;
   auto kern = fmha_fwd_kernel<D, BF16, HAS_BIAS>;
   constexpr int SMEM = fmha_smem_bytes<D>();
   static bool attr_set = false;

@@ -102,7 +102,9 @@ class CameraTables:
         if k not in self._bias:
             V = len(key[0])
             ce, cp = self._records(key, V, ph, pw, dev)
-            self._bias[k] = ops.eppa_tables(ce, cp, V // groups, ph, pw, eh, ew)
+            b1, b2 = ops.eppa_tables(ce, cp, V // groups, ph, pw, eh, ew)
+            # block-sparsity hints: most (query tile, key tile) pairs have no geometric correspondence at all
+            self._bias[k] = (b1, b2, ops.bias_tile_flags(b1), ops.bias_tile_flags(b2))
         return self._bias[k]
 
     def pe(self, key, ph, pw, eh, ew, freq_bands: Tensor, dev):
@@ -157,10 +159,13 @@ class WarpAttn(nn.Module):
         ph, pw, eh, ew = pers.H, pers.W, equi.H, equi.W
         P, E = ph * pw, eh * ew
         key, groups = CameraTables.dedup(cam_key, b)
-        bias1, bias2 = self.tables.bias(key, groups, ph, pw, eh, ew, dev)      # [G, E, m*P], [G, m*P, E]
+        bias1, bias2, flags1, flags2 = self.tables.bias(key, groups, ph, pw, eh, ew, dev)  # [G, E, m*P], [G, m*P, E]
         pers_pe, equi_pe = self.tables.pe(key, ph, pw, eh, ew, self.pe.freq_bands, dev)  # [G*m*P, C], [E, C]
         if m_loc != m:
             bias2 = bias2[:, v0 * P:(v0 + m_loc) * P]
+            # flag rows are 128-query tiles: usable for the local slice only when it starts on a tile boundary
+            flags2 = flags2[:, (v0 * P) // 128:((v0 + m_loc) * P + 127) // 128].contiguous() \
+                if (v0 * P) % 128 == 0 and (m_loc * P) % 128 == 0 else None
             pers_pe = pers_pe.reshape(groups, m * P, C)[:, v0 * P:(v0 + m_loc) * P].reshape(groups * m_loc * P, C)
             pers_pe = pers_pe if pers_pe.is_contiguous() else self._local_pe(pers_pe, (key, ph, pw, v0, m_loc))
         heads, d = w["heads"], C // w["heads"]
@@ -192,12 +197,12 @@ class WarpAttn(nn.Module):
 
         # direction 1 (modules.py:44-48): pano pixels query every view's pixels
         o1 = torch.empty((b, E, C), dtype=dt, device=dev)
-        ops.fmha(qkv_e[..., :C], k_all, v_all, o1, heads=heads, head_dim=d, scale=scale, bias=bias1)
+        ops.fmha(qkv_e[..., :C], k_all, v_all, o1, heads=heads, head_dim=d, scale=scale, bias=bias1, bias_flags=flags1)
         equi_out = finish(o1.reshape(Te, C), equi.t, Te)
         # direction 2 (modules.py:51-55): view pixels query the pano; reads the INPUT features
         o2 = torch.empty((b, m_loc * P, C), dtype=dt, device=dev)
         ops.fmha(qkv_p[..., :C], qkv_e[..., C:2 * C], qkv_e[..., 2 * C:], o2, heads=heads, head_dim=d, scale=scale,
-                 bias=bias2)
+                 bias=bias2, bias_flags=flags2)
         pers_out = finish(o2.reshape(Tp, C), pers.t, Tp)
         return Img(pers_out, b * m_loc, ph, pw), Img(equi_out, b, eh, ew)
 

@@ -21,7 +21,8 @@ from .eppa import CameraTables, WarpAttn
 
 
 class MultiViewBaseModel(nn.Module):
-    def __init__(self, unet, pano_unet, pers_cn=None, pano_cn=None, pano_pad=True, compute_dtype=torch.bfloat16):
+    def __init__(self, unet, pano_unet, pers_cn=None, pano_cn=None, pano_pad=True, compute_dtype=torch.bfloat16,
+                 overlap_branches=True):
         super().__init__()
         self.unet = unet
         self.pano_unet = pano_unet
@@ -29,6 +30,8 @@ class MultiViewBaseModel(nn.Module):
         self.pano_cn = pano_cn
         self.pano_pad = pano_pad
         self.compute_dtype = compute_dtype
+        self.overlap_branches = overlap_branches  # run the panorama branch on a second CUDA stream
+        self._side = None
         if self.unet is not None:  # MVGenModel.py:17-36
             self.cp_blocks_encoder = nn.ModuleList(
                 [WarpAttn(blk.downsamplers[-1].out_channels) for blk in unet.down_blocks if blk.downsamplers is not None])
@@ -101,9 +104,36 @@ class MultiViewBaseModel(nn.Module):
             pano.set_timesteps(timestep)
         pano.set_text(pano_prompt_embd.flatten(0, 1), pano_text_key)
 
+        # The two branches only meet inside EPPA. The panorama branch (batch b, many under-filled launches) runs on a
+        # side stream and the perspective branch on the caller's stream; they join before / fork after every fusion.
+        main = torch.cuda.current_stream()
+        two = bool(self.overlap_branches and has_pers)
+        if two and self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        side = self._side if two else main
+        keep = []  # tensors produced on `main` but consumed on `side`: kept alive until the next join
+
+        def fork():
+            if two:
+                side.wait_event(main.record_event())
+
+        def join():
+            if two:
+                main.wait_event(side.record_event())
+                keep.clear()
+
+        def fuse(block, h, p):
+            join()
+            h, p = block.forward_tokens(h, p, cam_key, par)
+            keep.append(p.t)
+            fork()
+            return h, p
+
+        fork()
         # conv_in (MVGenModel.py:85-91)
         h = pers.conv_in(latents.flatten(0, 1)) if has_pers else None
-        p = pano.conv_in(pano_latent.flatten(0, 1))
+        with torch.cuda.stream(side):
+            p = pano.conv_in(pano_latent.flatten(0, 1))
         skips, pano_skips = ([h] if has_pers else []), [p]
 
         # encoder (MVGenModel.py:98-152)
@@ -115,33 +145,37 @@ class MultiViewBaseModel(nn.Module):
                     if blk["attns"] is not None:
                         h = pers.transformer(h, blk["attns"][j])
                     skips.append(h)
-                p = pano.resnet(p, pres)
-                if pblk["attns"] is not None:
-                    p = pano.transformer(p, pblk["attns"][j])
+                with torch.cuda.stream(side):
+                    p = pano.resnet(p, pres)
+                    if pblk["attns"] is not None:
+                        p = pano.transformer(p, pblk["attns"][j])
                 pano_skips.append(p)
             if pblk["down"] is not None:
                 for j, pd in enumerate(pblk["down"]):
                     if has_pers:
                         h = pers.downsample(h, pers.p.down[i]["down"][j])
-                    p = pano.downsample(p, pd)
+                    with torch.cuda.stream(side):
+                        p = pano.downsample(p, pd)
                 if has_pers:
                     skips.append(h)
                 pano_skips.append(p)  # skips are taken BEFORE the fusion (MVGenModel.py:146-152)
                 if has_pers:
-                    h, p = self.cp_blocks_encoder[i].forward_tokens(h, p, cam_key, par)
+                    h, p = fuse(self.cp_blocks_encoder[i], h, p)
 
         # mid (MVGenModel.py:172-207)
         if has_pers:
             h = pers.resnet(h, pers.p.mid["resnets"][0])
-        p = pano.resnet(p, pano.p.mid["resnets"][0])
+        with torch.cuda.stream(side):
+            p = pano.resnet(p, pano.p.mid["resnets"][0])
         for i, pat in enumerate(pano.p.mid["attns"]):
             if has_pers:
                 h = pers.transformer(h, pers.p.mid["attns"][i])
                 h = pers.resnet(h, pers.p.mid["resnets"][i + 1])
-            p = pano.transformer(p, pat)
-            p = pano.resnet(p, pano.p.mid["resnets"][i + 1])
+            with torch.cuda.stream(side):
+                p = pano.transformer(p, pat)
+                p = pano.resnet(p, pano.p.mid["resnets"][i + 1])
         if has_pers:
-            h, p = self.cp_blocks_mid.forward_tokens(h, p, cam_key, par)
+            h, p = fuse(self.cp_blocks_mid, h, p)
 
         # decoder (MVGenModel.py:210-277)
         for i, pblk in enumerate(pano.p.up):
@@ -151,23 +185,27 @@ class MultiViewBaseModel(nn.Module):
                     h = pers.resnet(pers.concat(h, skips.pop()), blk["resnets"][j])
                     if blk["attns"] is not None:
                         h = pers.transformer(h, blk["attns"][j])
-                p = pano.resnet(pano.concat(p, pano_skips.pop()), pres)
-                if pblk["attns"] is not None:
-                    p = pano.transformer(p, pblk["attns"][j])
+                with torch.cuda.stream(side):
+                    p = pano.resnet(pano.concat(p, pano_skips.pop()), pres)
+                    if pblk["attns"] is not None:
+                        p = pano.transformer(p, pblk["attns"][j])
             if pblk["up"] is not None:
                 if has_pers:
-                    h, p = self.cp_blocks_decoder[i].forward_tokens(h, p, cam_key, par)  # fusion BEFORE the upsampler
+                    h, p = fuse(self.cp_blocks_decoder[i], h, p)  # fusion BEFORE the upsampler (MVGenModel.py:264-267)
                 for j, pu in enumerate(pblk["up"]):
                     if has_pers:
                         h = pers.upsample(h, pers.p.up[i]["up"][j])
-                    p = pano.upsample(p, pu)
+                    with torch.cuda.stream(side):
+                        p = pano.upsample(p, pu)
 
         # heads (MVGenModel.py:279-297)
         sample = None
         if has_pers:
             s = pers.conv_out(h)
             sample = s.reshape(b, m, *s.shape[1:]).to(latents.dtype)
-        ps = pano.conv_out(p)[:, None]
+        with torch.cuda.stream(side):
+            ps = pano.conv_out(p)[:, None]
+        join()
         if par is not None:
             sample, ps = par.gather_outputs(sample, ps, b_full, m_full)
         return sample, ps.to(pano_latent.dtype)

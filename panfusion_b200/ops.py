@@ -28,6 +28,23 @@ def _st():
     return C.c_void_p(_lib.stream_ptr())
 
 
+# per-shape tile choice measured on B200 by scripts/tune_gemm.py: (M, N, Kc, taps) -> block_n
+GEMM_LOG = None
+_TUNED: dict = {}
+
+
+def _load_tuning() -> None:
+    import json
+    from pathlib import Path
+    f = Path(__file__).with_name("gemm_tuning.json")
+    if f.exists():
+        for k, v in json.loads(f.read_text()).get("block_n", {}).items():
+            _TUNED[tuple(int(x) for x in k.split(","))] = int(v)
+
+
+_load_tuning()
+
+
 def pick_block_n(n: int, act: int = PF_ACT_NONE) -> int:
     return int(_lib.lib().pf_gemm_pick_block_n(int(n), int(act)))
 
@@ -52,7 +69,12 @@ def gemm_taps(A: Tensor, B: Tensor, out: Tensor, *, M: int, Kc: int, taps: Seque
     a.M, a.N, a.Kc, a.num_taps = int(M), B.shape[0], int(Kc), len(taps)
     for i, t in enumerate(taps):
         a.tap_off[i] = int(t)
+    if not block_n and act != PF_ACT_GEGLU:
+        block_n = _TUNED.get((int(M), B.shape[0], int(Kc), len(taps)), 0)
     a.block_n = int(block_n)
+    if GEMM_LOG is not None:
+        GEMM_LOG.append((int(M), B.shape[0], int(Kc), len(taps), int(act), image_map is not None,
+                         residual is not None, out.dtype == torch.float32))
     a.out, a.out_ld, a.out_dtype = out.data_ptr(), out.stride(0), _lib.dtype_code(out.dtype)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
@@ -72,8 +94,19 @@ def gemm_taps(A: Tensor, B: Tensor, out: Tensor, *, M: int, Kc: int, taps: Seque
     return out
 
 
+def bias_tile_flags(bias: Tensor) -> Tensor:
+    """bias fp32 [G, Lq, Lk] -> uint8 [G, ceil(Lq/128), ceil(Lk/64)], 1 where the tile is entirely -1."""
+    assert bias.dtype == torch.float32 and bias.dim() == 3 and bias.stride(2) == 1
+    G, Lq, Lk = bias.shape
+    flags = torch.empty((G, (Lq + 127) // 128, (Lk + 63) // 64), dtype=torch.uint8, device=bias.device)
+    _count(1)
+    _lib.check(_lib.lib().pf_bias_tile_flags(_vp(bias), G, Lq, Lk, bias.stride(1), C.c_int64(bias.stride(0)),
+                                             _vp(flags), _st()))
+    return flags
+
+
 def fmha(q: Tensor, k: Tensor, v: Tensor, out: Tensor, *, heads: int, head_dim: int, scale: float,
-         bias: Optional[Tensor] = None) -> Tensor:
+         bias: Optional[Tensor] = None, bias_flags: Optional[Tensor] = None) -> Tensor:
     """out[b, l, h*d:(h+1)*d] = softmax(q_h k_h^T * scale + bias) v_h; see pf_fmha_fwd.
 
     q: [B, Lq, >=H*d] view (last stride 1), k/v: [B, Lk, >=H*d] views — slices of a fused QKV buffer are fine.
@@ -99,6 +132,12 @@ def fmha(q: Tensor, k: Tensor, v: Tensor, out: Tensor, *, heads: int, head_dim: 
             a.bias_bstride, a.bias_ld = (bias.stride(0) if bias.shape[0] > 1 else 0), bias.stride(1)
         else:
             a.bias_bstride, a.bias_ld = 0, bias.stride(0)
+        if bias_flags is not None:
+            assert bias_flags.dtype == torch.uint8 and bias_flags.dim() == 3 and bias_flags.is_contiguous()
+            assert bias_flags.shape[1] == (Lq + 127) // 128 and bias_flags.shape[2] == (Lk + 63) // 64
+            a.bias_flags = bias_flags.data_ptr()
+            a.flags_bstride = bias_flags.stride(0) if (bias.dim() == 3 and bias.shape[0] > 1) else 0
+            a.flags_ld = bias_flags.stride(1)
     _count(1)
     _lib.check(_lib.lib().pf_fmha_fwd(C.byref(a), _st()))
     return out
