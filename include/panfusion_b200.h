@@ -146,11 +146,13 @@ int pf_bias_tile_flags(const float* bias, int G, int Lq, int Lk, int bias_ld, in
  * circularly extended by `circ` columns on each side — the reference normalises the padded tensor
  * (models/pano/MVGenModel.py:110-115 wraps each panorama ResnetBlock2D in utils/pano.py:74-105 pad/unpad), so
  * columns {0..circ-1, W-circ..W-1} count twice. ws: scratch of pf_groupnorm_ws_floats(N, groups) floats.
+ * counters: N ints that are ZERO on entry (the kernel restores them to zero; concurrent calls need distinct slots):
+ * the last CTA of each image reduces the partial sums in a fixed order, so the result is deterministic.
  * mean_rstd: [N, groups, 2] fp32 (mean, 1/sqrt(var + eps)), biased variance like torch.nn.GroupNorm.
  * ------------------------------------------------------------------------------------------------ */
 int pf_groupnorm_ws_floats(int N, int groups);
 int pf_groupnorm_stats(const void* x, int dtype, int N, int H, int W, int C, int ld, int groups, int circ,
-                       float eps, float* ws, float* mean_rstd, void* stream);
+                       float eps, float* ws, int* counters, float* mean_rstd, void* stream);
 
 /* GroupNorm-apply (+SiLU) fused with building the tap-GEMM A operand (replaces norm+nonlinearity of diffusers
  * ResnetBlock2D / Transformer2DModel.norm, pad_pano/unpad_pano utils/pano.py:74-105, Upsample2D's nearest x2,

@@ -44,7 +44,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 template <int D>
 __host__ __device__ constexpr int fmha_smem_bytes() {
-  return FA_BLOCK_M * D * 2 + FA_STAGES * 2 * FA_BLOCK_N * D * 2 + FA_BLOCK_M * FA_BLOCK_N * 2 + 1024 + 256;
+  return FA_BLOCK_M * D * 2 + FA_STAGES * 2 * FA_BLOCK_N * D * 2 + FA_BLOCK_M * FA_BLOCK_N * 2 + 256;
 }
 
 template <int D, bool BF16, bool HAS_BIAS>
@@ -60,8 +60,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int TMEM_COLS = 256;
   constexpr uint32_t TM_S0 = 0, TM_S1 = 64, TM_O = 128;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128 B swizzle atoms) is requested on the declaration; verified once, never padded for
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + Q_BYTES;                       // stage s: K at s*2*KV_BYTES, V right after
   uint8_t* sP = sKV + FA_STAGES * 2 * KV_BYTES;      // [128][64] 16-bit, SW128 K-major

@@ -39,25 +39,38 @@ __host__ __device__ constexpr int gemm_stage_bytes(int block_n) {
   return GEMM_BLOCK_M * GEMM_BLOCK_K * 2 + block_n * GEMM_BLOCK_K * 2;
 }
 __host__ __device__ constexpr int gemm_smem_bytes(int block_n, int stages) {
-  return stages * gemm_stage_bytes(block_n) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return stages * gemm_stage_bytes(block_n) + 128 /*barriers*/ + block_n * 4 /*bias row*/;
 }
 
-template <int BLOCK_N, int STAGES, bool BF16>
+// EPI_TMA: plain row map + 16-bit output. The output tile is staged in shared memory as BLOCK_N/32 sub-tiles of
+// [128 rows][32 cols] (64-byte rows, SWIZZLE_64B) and written with TMA tile stores (fully coalesced, rows >= M
+// clipped by the hardware); a 16-bit residual tile is TMA-prefetched into the same staging buffer at kernel start,
+// so it arrives under the main loop instead of as per-thread scattered loads in the epilogue.
+template <int BLOCK_N, int STAGES, bool BF16, bool EPI_TMA>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  const GemmKernelParams p) {
   constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGING_BYTES = EPI_TMA ? GEMM_BLOCK_M * BLOCK_N * 2 : 0;
+  constexpr int SUB_BYTES = GEMM_BLOCK_M * 64;  // one [128][32] 16-bit sub-tile
   constexpr int TMEM_COLS = gemm_tmem_cols(BLOCK_N);
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA M=128 needs N%16==0, N<=256");
+  static_assert(!EPI_TMA || BLOCK_N % 32 == 0, "staged epilogue works on 32-column sub-tiles");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  // 1024-byte alignment (128 B swizzle atoms) is requested on the declaration; verified once, never padded for
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* staging = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* res_full_bar = tmem_full_bar + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_full_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(staging + STAGING_BYTES + 128);  // [BLOCK_N]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -75,6 +88,8 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(res_full_bar, 1);
+    if constexpr (EPI_TMA) tma_prefetch_desc(&tmC);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -89,6 +104,14 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
+      if constexpr (EPI_TMA) {
+        if (p.residual) {
+          mbar_expect_tx(res_full_bar, STAGING_BYTES);
+#pragma unroll
+          for (int sub = 0; sub < BLOCK_N / 32; ++sub)
+            tma_load_2d(staging + sub * SUB_BYTES, &tmR, res_full_bar, n0 + sub * 32, m0);
+        }
+      }
       for (int kb = 0; kb < p.num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -142,13 +165,75 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (p.rowbias) {
       group = m / p.rows_per_group;
     }
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     const uint32_t taddr_row = tmem_base + (uint32_t(q * 32) << 16);
+    // bias row of this column tile -> shared memory while the main loop is still running
+    if (p.bias) {
+      for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) s_bias[i] = __ldg(p.bias + n0 + i);
+    }
+    named_bar_sync(1, 128);
 
-    constexpr bool kDummy = false;
-    (void)kDummy;
-    if (p.act == PF_ACT_GEGLU) {
+    if constexpr (EPI_TMA) {
+      if (!valid) group = 0;  // rows past M are computed (and clipped by the TMA store): keep their table reads in bounds
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      if (p.residual) mbar_wait(res_full_bar, 0);
+      const uint32_t sw = uint32_t((row >> 1) & 3);  // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr_row + c, v);
+        tmem_ld_wait();
+        float o[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[e]);
+        if (p.bias) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] += s_bias[c + e];
+        }
+        if (p.rowbias) {
+          const float* rb = p.rowbias + (long long)group * p.rowbias_ld + n0 + c;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] += __ldg(rb + e);
+        }
+        if (p.act == PF_ACT_SILU) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] = silu_f(o[e]);
+        } else if (p.act == PF_ACT_GELU) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] = gelu_erf_f(o[e]);
+        }
+        uint8_t* srow = staging + (c >> 5) * SUB_BYTES + row * 64;
+        const uint32_t q0 = uint32_t((c >> 4) & 1) * 2;  // first 16-byte chunk of this 16-column group in the 64 B row
+        uint4* s0 = reinterpret_cast<uint4*>(srow + (((q0 + 0) ^ sw) << 4));
+        uint4* s1 = reinterpret_cast<uint4*>(srow + (((q0 + 1) ^ sw) << 4));
+        if (p.residual) {
+          const uint4 r0 = *s0, r1 = *s1;
+          float2 f;
+          f = unpack2<BF16>(r0.x); o[0] += f.x; o[1] += f.y;
+          f = unpack2<BF16>(r0.y); o[2] += f.x; o[3] += f.y;
+          f = unpack2<BF16>(r0.z); o[4] += f.x; o[5] += f.y;
+          f = unpack2<BF16>(r0.w); o[6] += f.x; o[7] += f.y;
+          f = unpack2<BF16>(r1.x); o[8] += f.x; o[9] += f.y;
+          f = unpack2<BF16>(r1.y); o[10] += f.x; o[11] += f.y;
+          f = unpack2<BF16>(r1.z); o[12] += f.x; o[13] += f.y;
+          f = unpack2<BF16>(r1.w); o[14] += f.x; o[15] += f.y;
+        }
+        *s0 = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]), pack2<BF16>(o[4], o[5]),
+                         pack2<BF16>(o[6], o[7]));
+        *s1 = make_uint4(pack2<BF16>(o[8], o[9]), pack2<BF16>(o[10], o[11]), pack2<BF16>(o[12], o[13]),
+                         pack2<BF16>(o[14], o[15]));
+      }
+      fence_proxy_async_smem();           // generic-proxy writes -> visible to the TMA store
+      named_bar_sync(1, 128);             // the four epilogue warps only
+      if (warp == 2 && lane == 0) {
+#pragma unroll
+        for (int sub = 0; sub < BLOCK_N / 32; ++sub) tma_store_2d(&tmC, staging + sub * SUB_BYTES, n0 + sub * 32, m0);
+        tma_store_commit();
+        tma_store_wait_read();
+      }
+    } else if (p.act == PF_ACT_GEGLU) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
       constexpr int HALF = BLOCK_N / 2;
       const int on0 = n_tile * HALF;
       if constexpr (HALF % 16 == 0) {
@@ -165,8 +250,8 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               float a = __uint_as_float(va[e]);
               float g = __uint_as_float(vg[e]);
               if (p.bias) {
-                a += __ldg(p.bias + n0 + c + e);
-                g += __ldg(p.bias + n0 + HALF + c + e);
+                a += s_bias[c + e];
+                g += s_bias[HALF + c + e];
               }
               o[e] = a * gelu_erf_f(g);
             }
@@ -185,10 +270,48 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     } else {
+      // Direct path (convolutions: halo-dropping row map; fp32 outputs). Global operands of the epilogue are fetched
+      // ahead of use — the 16-bit residual through a 4-deep register ring started BEFORE the accumulator wait, the
+      // per-image row bias one chunk ahead — so their latency hides under the main loop / the previous chunk.
+      constexpr int NCH = BLOCK_N / 16;
+      const bool res16 = p.residual != nullptr && !p.res_f32 && valid;
+      const uint4* rsrc = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.residual) + orow * p.res_ld + n0);
+      const uint4 z4 = make_uint4(0, 0, 0, 0);
+      // residual: chunks c and c+1 in flight (rolled loop, explicit double buffer)
+      uint4 ra0 = z4, ra1 = z4, rb0 = z4, rb1 = z4;
+      if (res16) {
+        ra0 = __ldg(rsrc);
+        ra1 = __ldg(rsrc + 1);
+        if (NCH > 1) {
+          rb0 = __ldg(rsrc + 2);
+          rb1 = __ldg(rsrc + 3);
+        }
+      }
+      const float* rb_base = p.rowbias ? p.rowbias + (long long)(valid ? group : 0) * p.rowbias_ld + n0 : nullptr;
+      float4 rbn[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) rbn[e] = rb_base ? __ldg(reinterpret_cast<const float4*>(rb_base) + e) : make_float4(0, 0, 0, 0);
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 16) {
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int c = ci * 16;
         uint32_t v[16];
         tmem_ld16(taddr_row + c, v);
+        float4 rbc[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) rbc[e] = rbn[e];
+        if (rb_base && ci + 1 < NCH) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) rbn[e] = __ldg(reinterpret_cast<const float4*>(rb_base + c + 16) + e);
+        }
+        const uint4 r0 = ra0, r1 = ra1;
+        ra0 = rb0;
+        ra1 = rb1;
+        if (res16 && ci + 2 < NCH) {
+          rb0 = __ldg(rsrc + 2 * (ci + 2));
+          rb1 = __ldg(rsrc + 2 * (ci + 2) + 1);
+        }
         tmem_ld_wait();
         if (valid) {
           float o[16];
@@ -196,12 +319,16 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[e]);
           if (p.bias) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) o[e] += __ldg(p.bias + n0 + c + e);
+            for (int e = 0; e < 16; ++e) o[e] += s_bias[c + e];
           }
-          if (p.rowbias) {
-            const float* rb = p.rowbias + (long long)group * p.rowbias_ld + n0 + c;
+          if (rb_base) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) o[e] += __ldg(rb + e);
+            for (int e = 0; e < 4; ++e) {
+              o[4 * e] += rbc[e].x;
+              o[4 * e + 1] += rbc[e].y;
+              o[4 * e + 2] += rbc[e].z;
+              o[4 * e + 3] += rbc[e].w;
+            }
           }
           if (p.act == PF_ACT_SILU) {
 #pragma unroll
@@ -223,17 +350,15 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 o[4 * e + 3] += t.w;
               }
             } else {
-              const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.residual) +
-                                                               orow * p.res_ld + n0 + c);
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                uint4 t = r4[h];
-                float2 f;
-                f = unpack2<BF16>(t.x); o[8 * h + 0] += f.x; o[8 * h + 1] += f.y;
-                f = unpack2<BF16>(t.y); o[8 * h + 2] += f.x; o[8 * h + 3] += f.y;
-                f = unpack2<BF16>(t.z); o[8 * h + 4] += f.x; o[8 * h + 5] += f.y;
-                f = unpack2<BF16>(t.w); o[8 * h + 6] += f.x; o[8 * h + 7] += f.y;
-              }
+              float2 f;
+              f = unpack2<BF16>(r0.x); o[0] += f.x; o[1] += f.y;
+              f = unpack2<BF16>(r0.y); o[2] += f.x; o[3] += f.y;
+              f = unpack2<BF16>(r0.z); o[4] += f.x; o[5] += f.y;
+              f = unpack2<BF16>(r0.w); o[6] += f.x; o[7] += f.y;
+              f = unpack2<BF16>(r1.x); o[8] += f.x; o[9] += f.y;
+              f = unpack2<BF16>(r1.y); o[10] += f.x; o[11] += f.y;
+              f = unpack2<BF16>(r1.z); o[12] += f.x; o[13] += f.y;
+              f = unpack2<BF16>(r1.w); o[14] += f.x; o[15] += f.y;
             }
           }
           if (p.out_f32) {
@@ -260,9 +385,9 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool EPI_TMA>
 static int launch_gemm(const pf_gemm_args* a, const GemmKernelParams& kp, cudaStream_t st) {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC, tmR;
   {
     uint64_t dims[2] = {(uint64_t)a->Kc, (uint64_t)a->a_rows};
     uint64_t str[1] = {(uint64_t)a->a_ld * 2};
@@ -277,11 +402,25 @@ static int launch_gemm(const pf_gemm_args* a, const GemmKernelParams& kp, cudaSt
     int rc = make_tmap(&tmB, a->dtype, 2, a->B, dims, str, box, 128);
     if (rc) return rc;
   }
-  constexpr int SMEM = gemm_smem_bytes(BLOCK_N, STAGES);
+  tmC = tmA;
+  tmR = tmA;
+  if constexpr (EPI_TMA) {
+    uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M};
+    uint32_t box[2] = {32, GEMM_BLOCK_M};
+    uint64_t str[1] = {(uint64_t)a->out_ld * 2};
+    int rc = make_tmap(&tmC, a->dtype, 2, a->out, dims, str, box, 64);
+    if (rc) return rc;
+    if (a->residual) {
+      uint64_t rstr[1] = {(uint64_t)a->res_ld * 2};
+      rc = make_tmap(&tmR, a->dtype, 2, a->residual, dims, rstr, box, 64);
+      if (rc) return rc;
+    }
+  }
+  constexpr int SMEM = gemm_smem_bytes(BLOCK_N, STAGES) + (EPI_TMA ? GEMM_BLOCK_M * BLOCK_N * 2 : 0);
   const int m_tiles = (a->M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int grid = m_tiles * (a->N / BLOCK_N);
   if (a->dtype == PF_BF16) {
-    auto kern = gemm_taps_kernel<BLOCK_N, STAGES, true>;
+    auto kern = gemm_taps_kernel<BLOCK_N, STAGES, true, EPI_TMA>;
     static bool attr_set = false;
     if (!attr_set) {
       int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM),
@@ -289,9 +428,9 @@ static int launch_gemm(const pf_gemm_args* a, const GemmKernelParams& kp, cudaSt
       if (rc) return rc;
       attr_set = true;
     }
-    kern<<<grid, GEMM_THREADS, SMEM, st>>>(tmA, tmB, kp);
+    kern<<<grid, GEMM_THREADS, SMEM, st>>>(tmA, tmB, tmC, tmR, kp);
   } else {
-    auto kern = gemm_taps_kernel<BLOCK_N, STAGES, false>;
+    auto kern = gemm_taps_kernel<BLOCK_N, STAGES, false, EPI_TMA>;
     static bool attr_set = false;
     if (!attr_set) {
       int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM),
@@ -299,7 +438,7 @@ static int launch_gemm(const pf_gemm_args* a, const GemmKernelParams& kp, cudaSt
       if (rc) return rc;
       attr_set = true;
     }
-    kern<<<grid, GEMM_THREADS, SMEM, st>>>(tmA, tmB, kp);
+    kern<<<grid, GEMM_THREADS, SMEM, st>>>(tmA, tmB, tmC, tmR, kp);
   }
   PF_CHECK_LAUNCH("gemm_taps_kernel");
   return PF_OK;
@@ -373,11 +512,22 @@ extern "C" int pf_gemm_taps(const pf_gemm_args* a, void* stream) {
   kp.Hout = a->Hout;
   kp.Wout = a->Wout;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // staged TMA-store epilogue: plain row map, 16-bit output, 16-bit (or no) residual, no GEGLU
+  const bool epi_tma = a->map_mode == 0 && a->out_dtype == a->dtype && a->act != PF_ACT_GEGLU &&
+                       (!a->residual || a->res_dtype == a->dtype) && bn != 256 &&
+                       (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0;
+  if (epi_tma) {
+    switch (bn) {
+      case 64: return launch_gemm<64, 4, true>(a, kp, st);
+      case 128: return launch_gemm<128, 2, true>(a, kp, st);
+      case 160: return launch_gemm<160, 2, true>(a, kp, st);
+    }
+  }
   switch (bn) {
-    case 64: return launch_gemm<64, 4>(a, kp, st);
-    case 128: return launch_gemm<128, 3>(a, kp, st);
-    case 160: return launch_gemm<160, 3>(a, kp, st);
-    case 256: return launch_gemm<256, 2>(a, kp, st);
+    case 64: return launch_gemm<64, 4, false>(a, kp, st);
+    case 128: return launch_gemm<128, 3, false>(a, kp, st);
+    case 160: return launch_gemm<160, 3, false>(a, kp, st);
+    case 256: return launch_gemm<256, 2, false>(a, kp, st);
   }
   return PF_ERR_UNSUPPORTED;
 }

@@ -24,7 +24,8 @@ __device__ __forceinline__ int gn_chunks(int hw) {
 template <bool BF16>
 __global__ void __launch_bounds__(512)
 gn_partial_kernel(const uint16_t* __restrict__ x, int H, int W, int C, int ld, int groups, int circ,
-                  float* __restrict__ ws) {
+                  float* __restrict__ ws, int* __restrict__ counters, float count, float eps,
+                  float* __restrict__ mean_rstd) {
   extern __shared__ float s_acc[];  // [ppi][2][C] per-pixel-lane partials (fixed-order reduction: deterministic)
   const int vecs = C / 8;
   const int ppi = blockDim.x / vecs;
@@ -80,17 +81,21 @@ gn_partial_kernel(const uint16_t* __restrict__ x, int H, int W, int C, int ld, i
     o[0] = a;
     o[1] = b;
   }
-}
-
-__global__ void gn_finalize_kernel(const float* __restrict__ ws, int chunks, int groups, float count, float eps,
-                                   float* __restrict__ mean_rstd) {
-  const int n = blockIdx.x;
+  // The last CTA of image n to arrive reduces the chunk partials in a FIXED order (deterministic) and publishes
+  // mean / rstd — no separate finalize launch. counters[n] returns to 0 for the next use.
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&counters[n], 1) == chunks - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     double a = 0.0, b = 0.0;
     for (int c = 0; c < chunks; ++c) {
       const float* o = ws + (((size_t)n * chunks + c) * groups + g) * 2;
-      a += o[0];
-      b += o[1];
+      a += __ldcg(o);
+      b += __ldcg(o + 1);
     }
     const double mean = a / count;
     double var = b / count - mean * mean;
@@ -98,6 +103,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ ws, int chunks, int
     mean_rstd[((size_t)n * groups + g) * 2 + 0] = float(mean);
     mean_rstd[((size_t)n * groups + g) * 2 + 1] = float(1.0 / sqrt(var + double(eps)));
   }
+  if (threadIdx.x == 0) counters[n] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -253,9 +259,9 @@ layernorm_kernel(const uint16_t* __restrict__ x, int ldx, const float* __restric
 extern "C" int pf_groupnorm_ws_floats(int N, int groups) { return N * pf::GN_MAX_CHUNKS * groups * 2; }
 
 extern "C" int pf_groupnorm_stats(const void* x, int dtype, int N, int H, int W, int C, int ld, int groups, int circ,
-                                  float eps, float* ws, float* mean_rstd, void* stream) {
+                                  float eps, float* ws, int* counters, float* mean_rstd, void* stream) {
   using namespace pf;
-  PF_CHECK_ARG(x && ws && mean_rstd, "pf_groupnorm_stats: null pointer");
+  PF_CHECK_ARG(x && ws && counters && mean_rstd, "pf_groupnorm_stats: null pointer");
   PF_CHECK_ARG(dtype == PF_BF16 || dtype == PF_F16, "pf_groupnorm_stats: 16-bit dtype required");
   PF_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && groups > 0 && C % groups == 0 && C % 8 == 0 && ld % 8 == 0 &&
                    ld >= C && C / 8 <= 512,
@@ -271,14 +277,14 @@ extern "C" int pf_groupnorm_stats(const void* x, int dtype, int N, int H, int W,
   const int threads = vecs * ppi;
   dim3 grid(chunks, N);
   const size_t smem = 2 * (size_t)C * ppi * sizeof(float);
-  if (dtype == PF_BF16)
-    gn_partial_kernel<true><<<grid, threads, smem, st>>>(static_cast<const uint16_t*>(x), H, W, C, ld, groups, circ, ws);
-  else
-    gn_partial_kernel<false><<<grid, threads, smem, st>>>(static_cast<const uint16_t*>(x), H, W, C, ld, groups, circ, ws);
-  PF_CHECK_LAUNCH("gn_partial_kernel");
   const float count = float(H) * float(W + 2 * circ) * float(C / groups);
-  gn_finalize_kernel<<<N, 32, 0, st>>>(ws, chunks, groups, count, eps, mean_rstd);
-  PF_CHECK_LAUNCH("gn_finalize_kernel");
+  if (dtype == PF_BF16)
+    gn_partial_kernel<true><<<grid, threads, smem, st>>>(static_cast<const uint16_t*>(x), H, W, C, ld, groups, circ, ws,
+                                                         counters, count, eps, mean_rstd);
+  else
+    gn_partial_kernel<false><<<grid, threads, smem, st>>>(static_cast<const uint16_t*>(x), H, W, C, ld, groups, circ, ws,
+                                                          counters, count, eps, mean_rstd);
+  PF_CHECK_LAUNCH("gn_partial_kernel");
   return PF_OK;
 }
 

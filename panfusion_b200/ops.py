@@ -146,15 +146,32 @@ def fmha(q: Tensor, k: Tensor, v: Tensor, out: Tensor, *, heads: int, head_dim: 
 # ------------------------------------------------------------------------------------------------
 # normalisation / preparation
 # ------------------------------------------------------------------------------------------------
+_GN_COUNTERS: dict = {}
+_GN_SLOTS = 1 << 16
+
+
+def _gn_counter_slot(device, n: int) -> Tensor:
+    """n zeroed ints from a per-device ring (the kernel restores them to zero). Calls in flight at the same time —
+    the two branch streams — always get different slots; a slot is only reused ~65k images later."""
+    ent = _GN_COUNTERS.get(device)
+    if ent is None:
+        ent = _GN_COUNTERS[device] = [torch.zeros(_GN_SLOTS, dtype=torch.int32, device=device), 0]
+    buf, pos = ent
+    if pos + n > _GN_SLOTS:
+        pos = 0
+    ent[1] = pos + n
+    return buf[pos:pos + n]
+
+
 def groupnorm_stats(x: Tensor, N: int, H: int, W: int, groups: int, eps: float, circ: int = 0) -> Tensor:
     """x: [N*H*W, C] tokens -> mean_rstd [N, groups, 2] fp32 (statistics over the circularly extended image)."""
     Cc = x.shape[1]
     lib = _lib.lib()
     ws = torch.empty(lib.pf_groupnorm_ws_floats(N, groups), dtype=torch.float32, device=x.device)
     out = torch.empty((N, groups, 2), dtype=torch.float32, device=x.device)
-    _count(2)
+    _count(1)
     _lib.check(lib.pf_groupnorm_stats(_vp(x), _lib.dtype_code(x.dtype), N, H, W, Cc, x.stride(0), groups, circ,
-                                      _f(eps), _vp(ws), _vp(out), _st()))
+                                      _f(eps), _vp(ws), _vp(_gn_counter_slot(x.device, N)), _vp(out), _st()))
     return out
 
 
