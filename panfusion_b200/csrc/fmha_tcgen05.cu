@@ -17,7 +17,6 @@ namespace pf {
 
 constexpr int FA_BLOCK_M = 128;
 constexpr int FA_BLOCK_N = 64;
-constexpr int FA_STAGES = 4;
 constexpr int FA_THREADS = 192;
 
 struct FmhaParams {
@@ -43,38 +42,47 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 template <int D>
+__host__ __device__ constexpr int fa_stages() { return D == 64 ? 2 : 4; }
+template <int D>
 __host__ __device__ constexpr int fmha_smem_bytes() {
-  return FA_BLOCK_M * D * 2 + FA_STAGES * 2 * FA_BLOCK_N * D * 2 + FA_BLOCK_M * FA_BLOCK_N * 2 + 256;
+  return FA_BLOCK_M * D * 2 + fa_stages<D>() * 2 * FA_BLOCK_N * D * 2 + FA_BLOCK_M * FA_BLOCK_N * 2 + 256;
 }
 
+// O stays in TMEM for the whole KV loop (P V accumulates in place). The running maximum used for scaling is only
+// raised when a row's new maximum exceeds it by more than 2^8 ("lazy rescale"): softmax is shift-invariant, so any
+// reference value gives the same result as long as exp2 stays in range, and the O / l rescale (TMEM load-scale-store)
+// becomes a rare event instead of per-tile work. Without a per-thread fp32 O accumulator the kernel fits three CTAs
+// per SM (112 registers, 64 KB smem, 128 TMEM columns each): three softmax warps per scheduler hide the
+// exp / TMEM / barrier latencies of one another.
 template <int D, bool BF16, bool HAS_BIAS>
-__global__ void __launch_bounds__(FA_THREADS, 2)
+__global__ void __launch_bounds__(FA_THREADS, 3)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
   static_assert(D == 32 || D == 64, "head dim 32 (EPPA) or 64 (SD-2 UNet)");
+  constexpr int STAGES = fa_stages<D>();
   constexpr int Q_BYTES = FA_BLOCK_M * D * 2;
   constexpr int KV_BYTES = FA_BLOCK_N * D * 2;  // one of K or V
   constexpr int P_BYTES = FA_BLOCK_M * FA_BLOCK_N * 2;
-  constexpr uint32_t SW_LAYOUT = (D == 64) ? 2u : 4u;     // 128B / 64B swizzle
+  constexpr uint32_t SW_LAYOUT = (D == 64) ? 2u : 4u;           // 128B / 64B swizzle
   constexpr uint32_t SW_ATOM_BYTES = (D == 64) ? 1024u : 512u;  // 8 rows of D*2 bytes
-  constexpr int TMEM_COLS = 256;
-  constexpr uint32_t TM_S0 = 0, TM_S1 = 64, TM_O = 128;
+  constexpr int TMEM_COLS = 128;
+  constexpr uint32_t TM_S = 0, TM_O = 64;
+  constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
-  // 1024-byte alignment (128 B swizzle atoms) is requested on the declaration; verified once, never padded for
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw;
+  extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + Q_BYTES;                       // stage s: K at s*2*KV_BYTES, V right after
-  uint8_t* sP = sKV + FA_STAGES * 2 * KV_BYTES;      // [128][64] 16-bit, SW128 K-major
+  uint8_t* sKV = sQ + Q_BYTES;                   // stage s: K at s*2*KV_BYTES, V right after
+  uint8_t* sP = sKV + STAGES * 2 * KV_BYTES;     // [128][64] 16-bit, SW128 K-major
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = kv_full + FA_STAGES;
-  uint64_t* s_full = kv_empty + FA_STAGES;  // [2]
-  uint64_t* p_full = s_full + 2;
-  uint64_t* o_full = p_full + 1;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* kv_empty = kv_full + STAGES;
+  uint64_t* s_full = kv_empty + STAGES;
+  uint64_t* s_free = s_full + 1;   // 128 arrivals: S has been read out of TMEM
+  uint64_t* p_full = s_free + 1;   // 128 arrivals: P is in shared memory (and O was rescaled if needed)
+  uint64_t* o_done = p_full + 1;   // P V of the tile has completed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x % p.H;  // heads fastest: CTAs sharing a bias tile run together (L2 reuse)
@@ -88,14 +96,14 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < FA_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(&s_full[0], 1);
-    mbar_init(&s_full[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
     mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    mbar_init(o_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -112,8 +120,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_expect_tx(q_full, Q_BYTES);
       tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
       for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % FA_STAGES;
-        mbar_wait(&kv_empty[s], ((j / FA_STAGES) & 1) ^ 1);
+        const int s = j % STAGES;
+        mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
         mbar_expect_tx(&kv_full[s], 2 * KV_BYTES);
         uint8_t* dst = sKV + s * 2 * KV_BYTES;
         tma_load_4d(dst, &tmK, &kv_full[s], 0, h, j * FA_BLOCK_N, b);
@@ -127,31 +135,34 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint64_t qdesc = make_smem_desc(smem_u32(sQ), 16, SW_ATOM_BYTES, SW_LAYOUT);
       const uint64_t pdesc = make_smem_desc(smem_u32(sP), 16, 1024, 2);
       auto issue_qk = [&](int j) {
-        const int s = j % FA_STAGES;
-        mbar_wait(&kv_full[s], (j / FA_STAGES) & 1);
+        const int s = j % STAGES;
+        mbar_wait(&kv_full[s], (j / STAGES) & 1);
         tc_fence_after();
         const uint64_t kdesc = make_smem_desc(smem_u32(sKV + s * 2 * KV_BYTES), 16, SW_ATOM_BYTES, SW_LAYOUT);
-        const uint32_t td = tmem_base + ((j & 1) ? TM_S1 : TM_S0);
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) umma_f16(td, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
-        umma_commit(&s_full[j & 1]);
+        for (int k = 0; k < D / 16; ++k) umma_f16(tmem_base + TM_S, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        umma_commit(s_full);
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
       for (int j = 0; j < n_tiles; ++j) {
+        // S_j has been copied to registers: Q K^T of the next tile may overwrite it while the softmax runs
+        mbar_wait(s_free, j & 1);
+        tc_fence_after();
         if (j + 1 < n_tiles) issue_qk(j + 1);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const int s = j % FA_STAGES;
+        const int s = j % STAGES;
         // V tile [64 keys][D]: MN-major B operand; 8-key groups are SW_ATOM_BYTES apart (SBO); one atom along N
         const uint64_t vdesc =
             make_smem_desc(smem_u32(sKV + s * 2 * KV_BYTES + KV_BYTES), SW_ATOM_BYTES, SW_ATOM_BYTES, SW_LAYOUT);
 #pragma unroll
         for (int k = 0; k < FA_BLOCK_N / 16; ++k) {
           // P: +32 B per 16 keys inside the 128 B swizzle row; V: +16 key rows = 2 swizzle atoms
-          umma_f16(tmem_base + TM_O, pdesc + 2 * k, vdesc + uint64_t((2 * SW_ATOM_BYTES * k) >> 4), idesc_pv, k != 0);
+          umma_f16(tmem_base + TM_O, pdesc + 2 * k, vdesc + uint64_t((2 * SW_ATOM_BYTES * k) >> 4), idesc_pv,
+                   (j | k) != 0 ? 1u : 0u);
         }
-        umma_commit(o_full);
+        umma_commit(o_done);
         umma_commit(&kv_empty[s]);
       }
     }
@@ -161,35 +172,33 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int q = q0 + row;
     const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
     constexpr float LOG2E = 1.4426950408889634f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
-    float o_acc[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) o_acc[d] = 0.f;
+    float m_used = -INFINITY, l_run = 0.f;
     const float* bias_row = nullptr;
+    const uint8_t* flag_row = nullptr;
     if constexpr (HAS_BIAS) {
       const int qq = q < p.Lq ? q : p.Lq - 1;
       bias_row = p.bias + (long long)b * p.bias_bstride + (long long)qq * p.bias_ld;
-    }
-    const uint8_t* flag_row = nullptr;
-    if constexpr (HAS_BIAS) {
       if (p.bias_flags) flag_row = p.bias_flags + (long long)b * p.flags_bstride + (long long)qt * p.flags_ld;
     }
+    const float sc = HAS_BIAS ? 1.0f : p.scale_log2;
+
     for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
       float sv[FA_BLOCK_N];
       {
         uint32_t raw[32];
-        const uint32_t ts = lane_addr + ((j & 1) ? TM_S1 : TM_S0);
-        tmem_ld32(ts, raw);
+        tmem_ld32(lane_addr + TM_S, raw);
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 32; ++e) sv[e] = __uint_as_float(raw[e]);
-        tmem_ld32(ts + 32, raw);
+        tmem_ld32(lane_addr + TM_S + 32, raw);
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 32; ++e) sv[32 + e] = __uint_as_float(raw[e]);
       }
+      tc_fence_before();
+      mbar_arrive(s_free);
       const int k0 = j * FA_BLOCK_N;
       // sv <- logits in log2 units. Without bias the softmax scale is folded into the exp2 argument below (one FFMA
       // per element); with bias: t = s*scale*log2e + bias*log2e.
@@ -221,38 +230,51 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int e = 0; e < FA_BLOCK_N; ++e)
           if (k0 + e >= p.Lk) sv[e] = -INFINITY;
       }
-      // running max (raw logits when no bias: scale > 0 commutes with max)
-      float mx_raw = -INFINITY;
+      // tile maximum: 8 independent chains
+      float mxs[8];
 #pragma unroll
-      for (int e = 0; e < FA_BLOCK_N; ++e) mx_raw = fmaxf(mx_raw, sv[e]);
-      const float sc = HAS_BIAS ? 1.0f : p.scale_log2;
-      const float mx = fmaxf(m_run, mx_raw * sc);
-      const float alpha = fast_exp2(m_run - mx);
-      m_run = mx;
-      float psum = 0.f;
+      for (int i = 0; i < 8; ++i) mxs[i] = sv[i];
+#pragma unroll
+      for (int e = 8; e < FA_BLOCK_N; ++e) mxs[e & 7] = fmaxf(mxs[e & 7], sv[e]);
+      const float mx_tile = sc * fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                                       fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      // lazy rescale: raise the reference only when this row would otherwise exceed 2^8
+      const bool need = mx_tile > m_used + RESCALE_THRESHOLD;
+      bool o_waited = false;
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_new = need ? mx_tile : m_used;
+        const float alpha = fast_exp2(m_used - m_new);  // 1 for rows that keep their reference, 0 on the first tile
+        if (j > 0) {
+          mbar_wait(o_done, (j - 1) & 1);  // P V of tile j-1 has landed in O
+          tc_fence_after();
+          o_waited = true;
+          uint32_t raw[16];  // 16-column pieces: this path runs with the 64 logits of the tile live in registers
+#pragma unroll 1
+          for (int c = 0; c < D; c += 16) {
+            tmem_ld16(lane_addr + TM_O + c, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) raw[e] = __float_as_uint(__uint_as_float(raw[e]) * alpha);
+            tmem_st16(lane_addr + TM_O + c, raw);
+          }
+          tmem_st_wait();
+        }
+        l_run *= alpha;
+        m_used = m_new;
+      }
+      float ps[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[FA_BLOCK_N / 2];
 #pragma unroll
       for (int e = 0; e < FA_BLOCK_N; e += 2) {
-        const float p0 = fast_exp2(fmaf(sv[e], sc, -mx)), p1 = fast_exp2(fmaf(sv[e + 1], sc, -mx));
-        psum += p0 + p1;
+        const float p0 = fast_exp2(fmaf(sv[e], sc, -m_used)), p1 = fast_exp2(fmaf(sv[e + 1], sc, -m_used));
+        ps[(e >> 1) & 3] += p0 + p1;
         pk[e >> 1] = pack2<BF16>(p0, p1);
       }
-      l_run = l_run * alpha + psum;
-
-      if (j > 0) {
-        // fold P V of tile j-1 (this also proves the tensor core is done reading sP)
-        mbar_wait(o_full, (j - 1) & 1);
+      l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+      if (j > 0 && !o_waited) {
+        mbar_wait(o_done, (j - 1) & 1);  // the tensor core is done reading sP (tile j-1)
         tc_fence_after();
-        uint32_t raw[32];
-#pragma unroll
-        for (int c = 0; c < D; c += 32) {
-          tmem_ld32(lane_addr + TM_O + c, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o_acc[c + e] = o_acc[c + e] * alpha_prev + __uint_as_float(raw[e]);
-        }
       }
-      alpha_prev = alpha;
       // P row -> swizzled smem: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
       {
         uint8_t* prow = sP + row * 128;
@@ -266,29 +288,27 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    // last tile's P V
-    mbar_wait(o_full, (n_tiles - 1) & 1);
+    // normalise and store
+    mbar_wait(o_done, (n_tiles - 1) & 1);
     tc_fence_after();
     {
+      const float inv = 1.0f / l_run;
+      uint16_t* orow = static_cast<uint16_t*>(p.out) + ((long long)b * p.Lq + q) * p.out_ld + h * D;
       uint32_t raw[32];
 #pragma unroll
       for (int c = 0; c < D; c += 32) {
         tmem_ld32(lane_addr + TM_O + c, raw);
         tmem_ld_wait();
+        if (q < p.Lq) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) o_acc[c + e] = o_acc[c + e] * alpha_prev + __uint_as_float(raw[e]);
-      }
-    }
-    if (q < p.Lq) {
-      const float inv = 1.0f / l_run;
-      uint16_t* orow = static_cast<uint16_t*>(p.out) + ((long long)b * p.Lq + q) * p.out_ld + h * D;
-#pragma unroll
-      for (int c = 0; c < D; c += 8) {
-        uint4 v = make_uint4(pack2<BF16>(o_acc[c] * inv, o_acc[c + 1] * inv),
-                             pack2<BF16>(o_acc[c + 2] * inv, o_acc[c + 3] * inv),
-                             pack2<BF16>(o_acc[c + 4] * inv, o_acc[c + 5] * inv),
-                             pack2<BF16>(o_acc[c + 6] * inv, o_acc[c + 7] * inv));
-        *reinterpret_cast<uint4*>(orow + c) = v;
+          for (int e = 0; e < 32; e += 8) {
+            uint4 v = make_uint4(pack2<BF16>(__uint_as_float(raw[e]) * inv, __uint_as_float(raw[e + 1]) * inv),
+                                 pack2<BF16>(__uint_as_float(raw[e + 2]) * inv, __uint_as_float(raw[e + 3]) * inv),
+                                 pack2<BF16>(__uint_as_float(raw[e + 4]) * inv, __uint_as_float(raw[e + 5]) * inv),
+                                 pack2<BF16>(__uint_as_float(raw[e + 6]) * inv, __uint_as_float(raw[e + 7]) * inv));
+            *reinterpret_cast<uint4*>(orow + c + e) = v;
+          }
+        }
       }
     }
     tc_fence_before();

@@ -7,36 +7,16 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane),
 // warps 2..5 = epilogue (thread <-> accumulator row, TMEM lane quarter = warp_id % 4).
-#include "pf_common.cuh"
+#include <stdlib.h>
+
+#include "gemm_common.cuh"
 
 namespace pf {
 
-constexpr int GEMM_BLOCK_M = 128;
-constexpr int GEMM_BLOCK_K = 64;  // 64 x 16-bit = 128 B = one swizzle row
 constexpr int GEMM_THREADS = 192;
-
-struct GemmKernelParams {
-  int M, N, num_kb, kb_per_tap;
-  int tap_off[PF_MAX_TAPS];
-  void* out;
-  int out_ld;
-  int out_f32;
-  const float* bias;
-  const float* rowbias;
-  int rowbias_ld;
-  int rows_per_group;
-  const void* residual;
-  int res_ld;
-  int res_f32;
-  int act;
-  int map_mode, Hm, Wm, i0, j0, Hout, Wout;
-};
 
 __host__ __device__ constexpr int gemm_tmem_cols(int block_n) {
   return block_n <= 32 ? 32 : block_n <= 64 ? 64 : block_n <= 128 ? 128 : block_n <= 256 ? 256 : 512;
-}
-__host__ __device__ constexpr int gemm_stage_bytes(int block_n) {
-  return GEMM_BLOCK_M * GEMM_BLOCK_K * 2 + block_n * GEMM_BLOCK_K * 2;
 }
 __host__ __device__ constexpr int gemm_smem_bytes(int block_n, int stages) {
   return stages * gemm_stage_bytes(block_n) + 128 /*barriers*/ + block_n * 4 /*bias row*/;
@@ -516,6 +496,17 @@ extern "C" int pf_gemm_taps(const pf_gemm_args* a, void* stream) {
   const bool epi_tma = a->map_mode == 0 && a->out_dtype == a->dtype && a->act != PF_ACT_GEGLU &&
                        (!a->residual || a->res_dtype == a->dtype) && bn != 256 &&
                        (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0;
+  // default: persistent warp-specialised kernel (gemm_persist.cu); PF_GEMM_LEGACY=1 keeps the one-tile-per-CTA kernel
+  // below reachable for A/B debugging only
+  // Scheduling choice (measured on B200, scripts/gemm_micro.py): linear layers (short K, staged TMA-store epilogue)
+  // run best as ONE persistent CTA per SM with double-buffered accumulators; convolutions (long K, direct stores) run
+  // best as two co-resident one-tile CTAs per SM, whose two TMA producers keep more K-slabs in flight.
+  // PF_GEMM_SCHED=persistent|tile forces one of them (debugging / A-B timing only).
+  static const char* force = getenv("PF_GEMM_SCHED");
+  const int m_tiles_ = (a->M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  bool persistent = epi_tma && (long long)m_tiles_ * (a->N / bn) >= 2 * 148;
+  if (force) persistent = force[0] == 'p';
+  if (persistent) return launch_gemm_persistent(a, kp, bn, epi_tma, st);
   if (epi_tma) {
     switch (bn) {
       case 64: return launch_gemm<64, 4, true>(a, kp, st);

@@ -39,8 +39,7 @@ gn_partial_kernel(const uint16_t* __restrict__ x, int H, int W, int C, int ld, i
   for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
   {
     const uint16_t* base = x + (size_t)n * hw * ld + v * 8;
-    for (int p = p_begin + pl; p < p_end; p += ppi) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * ld));
+    auto accum = [&](const uint4& raw, int p) {
       float wgt = 1.f;
       if (circ > 0) {
         const int col = p % W;
@@ -55,7 +54,20 @@ gn_partial_kernel(const uint16_t* __restrict__ x, int H, int W, int C, int ld, i
         s[2 * e + 1] += wgt * f.y;
         q[2 * e + 1] += wgt * f.y * f.y;
       }
+    };
+    int p = p_begin + pl;
+    // four independent 16-byte loads in flight per thread
+    for (; p + 3 * ppi < p_end; p += 4 * ppi) {
+      const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * ld));
+      const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + ppi) * ld));
+      const uint4 r2 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + 2 * ppi) * ld));
+      const uint4 r3 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + 3 * ppi) * ld));
+      accum(r0, p);
+      accum(r1, p + ppi);
+      accum(r2, p + 2 * ppi);
+      accum(r3, p + 3 * ppi);
     }
+    for (; p < p_end; p += ppi) accum(__ldg(reinterpret_cast<const uint4*>(base + (size_t)p * ld)), p);
     float* mine = s_acc + (size_t)pl * 2 * C;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -120,25 +132,36 @@ struct PrepParams {
   long long total_vecs;  // N * phases * Ho * Wo * C/8
 };
 
+// grid = (ceil(Wo * C/8 / 256), N * phases * Ho): one output row per blockIdx.y, so the per-channel scale/shift of the
+// row's image is built once per CTA in shared memory and the inner loop is load -> 8 FMA (+SiLU) -> store.
 template <bool BF16>
 __global__ void __launch_bounds__(256) conv_prep_kernel(const PrepParams p) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.total_vecs) return;
+  extern __shared__ float s_ss[];  // [2][C] scale, shift
   const int vecs = p.C / 8;
-  const int v = int(idx % vecs);
-  long long pos = idx / vecs;
-  const int j = int(pos % p.Wo);
-  pos /= p.Wo;
-  const int i = int(pos % p.Ho);
-  pos /= p.Ho;
-  const int n = int(pos % p.N);
-  const int ph = int(pos / p.N);  // phase index (0 when phases == 1)
-  // position in the (upsampled, circularly extended) image, before the zero halo
+  int rowid = blockIdx.y;
+  const int i = rowid % p.Ho;
+  rowid /= p.Ho;
+  const int n = rowid % p.N;
+  const int ph = rowid / p.N;
+  if (p.mean_rstd) {
+    const int cpg = p.C / p.groups;
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+      const int g = c / cpg;
+      const float mean = __ldg(p.mean_rstd + ((size_t)n * p.groups + g) * 2);
+      const float rstd = __ldg(p.mean_rstd + ((size_t)n * p.groups + g) * 2 + 1);
+      const float sc = rstd * __ldg(p.gamma + c);
+      s_ss[c] = sc;
+      s_ss[p.C + c] = __ldg(p.beta + c) - mean * sc;
+    }
+    __syncthreads();
+  }
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.Wo * vecs) return;
+  const int j = idx / vecs, v = idx - j * vecs;
   const int We = p.W + 2 * p.circ;
   const int Hu = p.H * p.up, Wu = We * p.up;
   int yy, xx;
   if (p.phases == 4) {
-    // padded image index (2i + py, 2j + px), halo of 1 -> source (yy, xx) = that - 1
     yy = 2 * i + (ph >> 1) - 1;
     xx = 2 * j + (ph & 1) - 1;
   } else {
@@ -162,15 +185,10 @@ __global__ void __launch_bounds__(256) conv_prep_kernel(const PrepParams p) {
         f[2 * e + 1] = t.y;
       }
       if (p.mean_rstd) {
-        const int cpg = p.C / p.groups;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = v * 8 + e;
-          const int g = c / cpg;
-          const float mean = __ldg(p.mean_rstd + ((size_t)n * p.groups + g) * 2);
-          const float rstd = __ldg(p.mean_rstd + ((size_t)n * p.groups + g) * 2 + 1);
-          f[e] = (f[e] - mean) * rstd * __ldg(p.gamma + c) + __ldg(p.beta + c);
-        }
+        const float4 s0 = *reinterpret_cast<const float4*>(s_ss + v * 8), s1 = *reinterpret_cast<const float4*>(s_ss + v * 8 + 4);
+        const float4 h0 = *reinterpret_cast<const float4*>(s_ss + p.C + v * 8), h1 = *reinterpret_cast<const float4*>(s_ss + p.C + v * 8 + 4);
+        f[0] = fmaf(f[0], s0.x, h0.x); f[1] = fmaf(f[1], s0.y, h0.y); f[2] = fmaf(f[2], s0.z, h0.z); f[3] = fmaf(f[3], s0.w, h0.w);
+        f[4] = fmaf(f[4], s1.x, h1.x); f[5] = fmaf(f[5], s1.y, h1.y); f[6] = fmaf(f[6], s1.z, h1.z); f[7] = fmaf(f[7], s1.w, h1.w);
       }
       if (p.act == PF_ACT_SILU) {
 #pragma unroll
@@ -182,7 +200,7 @@ __global__ void __launch_bounds__(256) conv_prep_kernel(const PrepParams p) {
       outv = raw;
     }
   }
-  *reinterpret_cast<uint4*>(p.out + (size_t)(idx / vecs) * p.C + v * 8) = outv;
+  *reinterpret_cast<uint4*>(p.out + ((size_t)blockIdx.y * p.Wo + j) * p.C + v * 8) = outv;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -193,63 +211,72 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const uint16_t* __restrict__ x, int ldx, const float* __restrict__ pe, int pe_rows, int T, int C,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                  uint16_t* __restrict__ out, int ldo) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= T) return;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int vecs = C / 8;
-  float f[MAXV][8];
-  float sum = 0.f;
-  const uint16_t* xr = x + (size_t)warp * ldx;
-  const float* per = pe ? pe + (size_t)(warp % pe_rows) * C : nullptr;
-#pragma unroll
-  for (int r = 0; r < MAXV; ++r) {
-    const int v = lane + r * 32;
-    if (v < vecs) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
-      const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 t = unpack2<BF16>(w4[e]);
-        f[r][2 * e] = t.x;
-        f[r][2 * e + 1] = t.y;
-      }
-      if (per) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(per + v * 8));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(per + v * 8 + 4));
-        f[r][0] += a.x; f[r][1] += a.y; f[r][2] += a.z; f[r][3] += a.w;
-        f[r][4] += b.x; f[r][5] += b.y; f[r][6] += b.z; f[r][7] += b.w;
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) sum += f[r][e];
-    }
+  // affine parameters staged once per CTA in shared memory (each warp then visits many tokens)
+  extern __shared__ float s_gb[];  // [2][C]
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_gb[c] = __ldg(gamma + c);
+    s_gb[C + c] = __ldg(beta + c);
   }
-  const float mean = warp_sum(sum) / float(C);
-  float sq = 0.f;
+  __syncthreads();
+  for (int tok = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tok < T; tok += warps_total) {
+    float f[MAXV][8];
+    float sum = 0.f;
+    const uint16_t* xr = x + (size_t)tok * ldx;
+    const float* per = pe ? pe + (size_t)(tok % pe_rows) * C : nullptr;
 #pragma unroll
-  for (int r = 0; r < MAXV; ++r) {
-    const int v = lane + r * 32;
-    if (v < vecs) {
+    for (int r = 0; r < MAXV; ++r) {
+      const int v = lane + r * 32;
+      if (v < vecs) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+        const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float d = f[r][e] - mean;
-        sq += d * d;
+        for (int e = 0; e < 4; ++e) {
+          const float2 t = unpack2<BF16>(w4[e]);
+          f[r][2 * e] = t.x;
+          f[r][2 * e + 1] = t.y;
+        }
+        if (per) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(per + v * 8));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(per + v * 8 + 4));
+          f[r][0] += a.x; f[r][1] += a.y; f[r][2] += a.z; f[r][3] += a.w;
+          f[r][4] += b.x; f[r][5] += b.y; f[r][6] += b.z; f[r][7] += b.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += f[r][e];
       }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(sq) / float(C) + eps);
-  uint16_t* orow = out + (size_t)warp * ldo;
+    const float mean = warp_sum(sum) / float(C);
+    float sq = 0.f;
 #pragma unroll
-  for (int r = 0; r < MAXV; ++r) {
-    const int v = lane + r * 32;
-    if (v < vecs) {
-      float o[8];
+    for (int r = 0; r < MAXV; ++r) {
+      const int v = lane + r * 32;
+      if (v < vecs) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = v * 8 + e;
-        o[e] = (f[r][e] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+        for (int e = 0; e < 8; ++e) {
+          const float d = f[r][e] - mean;
+          sq += d * d;
+        }
       }
-      *reinterpret_cast<uint4*>(orow + v * 8) = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]),
-                                                           pack2<BF16>(o[4], o[5]), pack2<BF16>(o[6], o[7]));
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / float(C) + eps);
+    uint16_t* orow = out + (size_t)tok * ldo;
+#pragma unroll
+    for (int r = 0; r < MAXV; ++r) {
+      const int v = lane + r * 32;
+      if (v < vecs) {
+        const float4 ga = *reinterpret_cast<const float4*>(s_gb + v * 8), gb = *reinterpret_cast<const float4*>(s_gb + v * 8 + 4);
+        const float4 ba = *reinterpret_cast<const float4*>(s_gb + C + v * 8), bb4 = *reinterpret_cast<const float4*>(s_gb + C + v * 8 + 4);
+        const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const float bb[8] = {ba.x, ba.y, ba.z, ba.w, bb4.x, bb4.y, bb4.z, bb4.w};
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (f[r][e] - mean) * rstd * gg[e] + bb[e];
+        *reinterpret_cast<uint4*>(orow + v * 8) = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]),
+                                                             pack2<BF16>(o[4], o[5]), pack2<BF16>(o[6], o[7]));
+      }
     }
   }
 }
@@ -269,7 +296,7 @@ extern "C" int pf_groupnorm_stats(const void* x, int dtype, int N, int H, int W,
   PF_CHECK_ARG(circ >= 0 && circ <= W, "pf_groupnorm_stats: circ=%d out of range", circ);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int hw = H * W;
-  int chunks = hw / 64;
+  int chunks = hw / 16;  // >= 16 pixels per CTA; small images still spread over several SMs
   chunks = chunks < 1 ? 1 : (chunks > GN_MAX_CHUNKS ? GN_MAX_CHUNKS : chunks);
   const int vecs = C / 8;
   int ppi = 256 / vecs;
@@ -316,11 +343,20 @@ extern "C" int pf_conv_prep(const void* x, void* out, int dtype, int N, int H, i
     p.Wo = Wu + 2 * halo;
   }
   p.total_vecs = (long long)N * phases * p.Ho * p.Wo * (C / 8);
-  const long long blocks = (p.total_vecs + 255) / 256;
-  PF_CHECK_ARG(blocks < (1LL << 31), "pf_conv_prep: tensor too large");
+  const long long rows = (long long)N * phases * p.Ho;
+  PF_CHECK_ARG(rows <= 2147483647LL / 1 && rows > 0, "pf_conv_prep: tensor too large");
+  const size_t smem = mean_rstd ? 2 * (size_t)C * sizeof(float) : 0;
+  PF_CHECK_ARG(smem <= 48 * 1024, "pf_conv_prep: C=%d too large", C);
+  dim3 grid((unsigned)((p.Wo * (C / 8) + 255) / 256), (unsigned)rows);
+  PF_CHECK_ARG(rows <= 65535LL * 32768LL, "pf_conv_prep: too many rows");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == PF_BF16) conv_prep_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(p);
-  else conv_prep_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(p);
+  if (rows > 65535) {
+    // gridDim.y limit: fold rows into x is not needed for UNet shapes (N*(H+2) <= 65535); refuse loudly otherwise
+    set_error("pf_conv_prep: N*phases*Ho = %lld exceeds 65535", rows);
+    return PF_ERR_UNSUPPORTED;
+  }
+  if (dtype == PF_BF16) conv_prep_kernel<true><<<grid, 256, smem, st>>>(p);
+  else conv_prep_kernel<false><<<grid, 256, smem, st>>>(p);
   PF_CHECK_LAUNCH("conv_prep_kernel");
   return PF_OK;
 }
@@ -334,11 +370,12 @@ extern "C" int pf_layernorm(const void* x, int ldx, void* out, int ldo, int dtyp
                "pf_layernorm: bad shape T=%d C=%d", T, C);
   PF_CHECK_ARG(!pe || pe_rows > 0, "pf_layernorm: pe_rows must be positive");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int blocks = (T + 7) / 8;
+  int blocks = (T + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;  // warps loop over tokens (affine parameters stay in registers)
   const uint16_t* xi = static_cast<const uint16_t*>(x);
   uint16_t* xo = static_cast<uint16_t*>(out);
   const int rounds = (C / 8 + 31) / 32;
-#define PF_LN(BF, MV) layernorm_kernel<BF, MV><<<blocks, 256, 0, st>>>(xi, ldx, pe, pe_rows, T, C, gamma, beta, eps, xo, ldo)
+#define PF_LN(BF, MV) layernorm_kernel<BF, MV><<<blocks, 256, 2 * (size_t)C * sizeof(float), st>>>(xi, ldx, pe, pe_rows, T, C, gamma, beta, eps, xo, ldo)
   if (dtype == PF_BF16) {
     if (rounds <= 2) PF_LN(true, 2); else if (rounds <= 5) PF_LN(true, 5); else PF_LN(true, 8);
   } else {
