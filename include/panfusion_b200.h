@@ -176,11 +176,11 @@ int pf_layernorm(const void* x, int ldx, void* out, int ldo, int dtype, int T, i
 int pf_conv_in(const float* x, const float* w, const float* bias, void* out, int dtype, int N, int Cin, int H, int W,
                int Cout, int circ, void* stream);
 
-/* conv_norm_out -> SiLU -> conv_out (MVGenModel.py:279-295): tokens [N,H,W,C] 16-bit -> NCHW fp32 [N,Cout<=4,H,W];
- * mean_rstd from pf_groupnorm_stats (circ = 0: the reference normalises the un-padded tensor at :288). */
-int pf_conv_out(const void* x, int ld, int dtype, const float* mean_rstd, const float* gamma, const float* beta,
-                int groups, const float* w, const float* bias, float* out, int N, int H, int W, int C, int Cout,
-                int circ, void* stream);
+/* conv_out (MVGenModel.py:279-295) over the PREPARED tensor: xp = pf_conv_prep(conv_norm_out statistics of the
+ * un-padded tensor as the reference does at :288, SiLU, circ, halo = 1) of shape [N, H+2, W+2*circ+2, C] 16-bit
+ * -> NCHW fp32 [N, Cout<=4, H, W]; circ = 1 for the panorama (pad_pano(1) -> conv -> unpad_pano(1)). */
+int pf_conv_out(const void* xp, int dtype, const float* w, const float* bias, float* out, int N, int H, int W, int C,
+                int Cout, int circ, void* stream);
 
 /* strided 2-D copy of 16-bit rows (skip concatenation, torch.cat at MVGenModel.py:223,231,246,254) */
 int pf_copy2d(const void* src, int src_ld, void* dst, int dst_ld, long long rows, int cols, void* stream);

@@ -64,61 +64,47 @@ conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv_out: tokens [N,H,W,C] -> GroupNorm -> SiLU -> conv 3x3 (C -> Cout<=4) -> NCHW fp32 (MVGenModel.py:279-295).
-// one warp per output pixel; weights fp32 [Cout, C, 3, 3] re-laid in smem as [tap][Cout][C].
+// conv_out: 3x3 conv (C -> Cout<=4) over the PREPARED input (conv_norm_out + SiLU already applied by pf_conv_prep,
+// zero halo of 1, panorama circularly extended by `circ` columns) -> NCHW fp32 (MVGenModel.py:279-295).
+// One warp per output pixel, lanes stride over channel pairs; weights fp32 [Cout, C, 3, 3] re-laid in smem as
+// [tap][Cout][C]. Reading the prepared tensor avoids re-evaluating GroupNorm+SiLU for each of the 9 taps.
 // ------------------------------------------------------------------------------------------------
 constexpr int CONV_OUT_PIX_PER_BLOCK = 64;
 
 template <bool BF16>
 __global__ void __launch_bounds__(256)
-conv_out_kernel(const uint16_t* __restrict__ x, int ld, const float* __restrict__ mean_rstd,
-                const float* __restrict__ gamma, const float* __restrict__ beta, int groups,
-                const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out, int N, int H,
-                int W, int C, int Cout, int circ) {
-  extern __shared__ float s_w[];  // [9][Cout][C] + scale[C] + shift[C] per image handled by this block
-  float* s_scale = s_w + 9 * Cout * C;
-  float* s_shift = s_scale + C;
+conv_out_kernel(const uint16_t* __restrict__ xp, const float* __restrict__ w, const float* __restrict__ bias,
+                float* __restrict__ out, int N, int H, int W, int C, int Cout, int circ) {
+  extern __shared__ float s_w[];  // [9][Cout][C]
   const int n = blockIdx.y;
   for (int i = threadIdx.x; i < 9 * Cout * C; i += blockDim.x) {
     const int c = i % C, co = (i / C) % Cout, tap = i / (C * Cout);
     s_w[i] = w[((size_t)co * C + c) * 9 + tap];
   }
-  const int cpg = C / groups;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float mean = mean_rstd[((size_t)n * groups + g) * 2], rstd = mean_rstd[((size_t)n * groups + g) * 2 + 1];
-    const float sc = rstd * gamma[c];
-    s_scale[c] = sc;
-    s_shift[c] = beta[c] - mean * sc;
-  }
   __syncthreads();
+  const int Hp = H + 2, Wp = W + 2 * circ + 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int pi = warp; pi < CONV_OUT_PIX_PER_BLOCK; pi += (blockDim.x >> 5)) {
-  const int pix = blockIdx.x * CONV_OUT_PIX_PER_BLOCK + pi;
-  if (pix >= H * W) break;
-  const int yy = pix / W, xx = pix % W;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int dy = 0; dy < 3; ++dy) {
-    const int sy = yy + dy - 1;
-    if (sy < 0 || sy >= H) continue;
-    for (int dx = 0; dx < 3; ++dx) {
-      int sx = xx + dx - 1;
-      if (circ) sx = sx < 0 ? sx + W : (sx >= W ? sx - W : sx);
-      else if (sx < 0 || sx >= W) continue;
-      const uint16_t* xr = x + ((size_t)n * H * W + (size_t)sy * W + sx) * ld;
-      const float* wt = s_w + (dy * 3 + dx) * Cout * C;
-      for (int c = lane * 2; c < C; c += 64) {
-        const float2 f = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(xr + c));
-        const float a0 = silu_f(f.x * s_scale[c] + s_shift[c]);
-        const float a1 = silu_f(f.y * s_scale[c + 1] + s_shift[c + 1]);
-        for (int co = 0; co < Cout; ++co) acc[co] += a0 * wt[co * C + c] + a1 * wt[co * C + c + 1];
+    const int pix = blockIdx.x * CONV_OUT_PIX_PER_BLOCK + pi;
+    if (pix >= H * W) break;
+    const int yy = pix / W, xx = pix % W;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const uint16_t* xr = xp + (((size_t)n * Hp + yy + dy) * Wp + xx + circ + dx) * C;
+        const float* wt = s_w + (dy * 3 + dx) * Cout * C;
+        for (int c = lane * 2; c < C; c += 64) {
+          const float2 f = unpack2<BF16>(__ldg(reinterpret_cast<const uint32_t*>(xr + c)));
+          for (int co = 0; co < Cout; ++co) acc[co] = fmaf(f.x, wt[co * C + c], fmaf(f.y, wt[co * C + c + 1], acc[co]));
+        }
       }
     }
-  }
-  for (int co = 0; co < Cout; ++co) {
-    const float v = warp_sum(acc[co]);
-    if (lane == 0) out[(((size_t)n * Cout + co) * H + yy) * W + xx] = v + (bias ? bias[co] : 0.f);
-  }
+    for (int co = 0; co < Cout; ++co) {
+      const float v = warp_sum(acc[co]);
+      if (lane == 0) out[(((size_t)n * Cout + co) * H + yy) * W + xx] = v + (bias ? bias[co] : 0.f);
+    }
   }
 }
 
@@ -205,16 +191,14 @@ extern "C" int pf_conv_in(const float* x, const float* w, const float* bias, voi
   return PF_OK;
 }
 
-extern "C" int pf_conv_out(const void* x, int ld, int dtype, const float* mean_rstd, const float* gamma,
-                           const float* beta, int groups, const float* w, const float* bias, float* out, int N, int H,
-                           int W, int C, int Cout, int circ, void* stream) {
+extern "C" int pf_conv_out(const void* xp, int dtype, const float* w, const float* bias, float* out, int N, int H, int W,
+                           int C, int Cout, int circ, void* stream) {
   using namespace pf;
-  PF_CHECK_ARG(x && mean_rstd && gamma && beta && w && out, "pf_conv_out: null pointer");
+  PF_CHECK_ARG(xp && w && out, "pf_conv_out: null pointer");
   PF_CHECK_ARG(dtype == PF_BF16 || dtype == PF_F16, "pf_conv_out: 16-bit input dtype required");
-  PF_CHECK_ARG(N > 0 && N <= 65535 && H > 0 && W > 0 && C % 2 == 0 && C % groups == 0 && Cout >= 1 && Cout <= 4 &&
-                   ld >= C && ld % 2 == 0,
+  PF_CHECK_ARG(N > 0 && N <= 65535 && H > 0 && W > 0 && C % 2 == 0 && Cout >= 1 && Cout <= 4 && circ >= 0,
                "pf_conv_out: bad shape");
-  const size_t smem = ((size_t)9 * Cout * C + 2 * C) * sizeof(float);
+  const size_t smem = (size_t)9 * Cout * C * sizeof(float);
   PF_CHECK_ARG(smem <= 200 * 1024, "pf_conv_out: C=%d too large", C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid((H * W + CONV_OUT_PIX_PER_BLOCK - 1) / CONV_OUT_PIX_PER_BLOCK, N);
@@ -222,11 +206,11 @@ extern "C" int pf_conv_out(const void* x, int ld, int dtype, const float* mean_r
   if (dtype == PF_BF16) {
     auto k = conv_out_kernel<true>;
     if ((rc = check_cuda(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv_out attr"))) return rc;
-    k<<<grid, 256, smem, st>>>(static_cast<const uint16_t*>(x), ld, mean_rstd, gamma, beta, groups, w, bias, out, N, H, W, C, Cout, circ);
+    k<<<grid, 256, smem, st>>>(static_cast<const uint16_t*>(xp), w, bias, out, N, H, W, C, Cout, circ);
   } else {
     auto k = conv_out_kernel<false>;
     if ((rc = check_cuda(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv_out attr"))) return rc;
-    k<<<grid, 256, smem, st>>>(static_cast<const uint16_t*>(x), ld, mean_rstd, gamma, beta, groups, w, bias, out, N, H, W, C, Cout, circ);
+    k<<<grid, 256, smem, st>>>(static_cast<const uint16_t*>(xp), w, bias, out, N, H, W, C, Cout, circ);
   }
   PF_CHECK_LAUNCH("conv_out_kernel");
   return PF_OK;

@@ -209,9 +209,11 @@ class Branch:
 
     def conv_out(self, x: Img) -> Tensor:
         p = self.p
+        c = 1 if self.circ else 0
         stats = ops.groupnorm_stats(x.t, x.N, x.H, x.W, p.groups, p.norm_out.eps, 0)  # un-padded (MVGenModel.py:288)
-        return ops.conv_out(x.t, x.N, x.H, x.W, stats, p.norm_out.g, p.norm_out.b, p.groups, p.conv_out_w,
-                            p.conv_out_b, self.circ)
+        xp = ops.conv_prep(x.t, x.N, x.H, x.W, stats=stats, gamma=p.norm_out.g, beta=p.norm_out.b, groups=p.groups,
+                           act=ops.PF_ACT_SILU, circ=c, halo=1)
+        return ops.conv_out(xp, x.N, x.H, x.W, p.conv_out_w, p.conv_out_b, c)
 
     def resnet(self, x: Img, r: _Resnet) -> Img:
         """ResnetBlock2D; panorama: pad_pano(2) -> block -> unpad_pano(2) (MVGenModel.py:110-115)."""

@@ -219,14 +219,14 @@ def conv_in(x: Tensor, w: Tensor, b: Optional[Tensor], dtype: torch.dtype, circ:
     return out
 
 
-def conv_out(x: Tensor, N: int, H: int, W: int, stats: Tensor, gamma: Tensor, beta: Tensor, groups: int, w: Tensor,
-             b: Optional[Tensor], circ: bool) -> Tensor:
-    """tokens -> GroupNorm -> SiLU -> 3x3 conv -> NCHW fp32 [N, Cout, H, W]."""
-    Cc, Cout = x.shape[1], w.shape[0]
-    out = torch.empty((N, Cout, H, W), dtype=torch.float32, device=x.device)
+def conv_out(xp: Tensor, N: int, H: int, W: int, w: Tensor, b: Optional[Tensor], circ: int) -> Tensor:
+    """xp = conv_prep(.., GroupNorm + SiLU, circ, halo=1) [N*(H+2)*(W+2*circ+2), C] -> NCHW fp32 [N, Cout, H, W]."""
+    Cc, Cout = xp.shape[1], w.shape[0]
+    assert xp.shape[0] == N * (H + 2) * (W + 2 * circ + 2) and xp.is_contiguous()
+    out = torch.empty((N, Cout, H, W), dtype=torch.float32, device=xp.device)
     _count(1)
-    _lib.check(_lib.lib().pf_conv_out(_vp(x), x.stride(0), _lib.dtype_code(x.dtype), _vp(stats), _vp(gamma), _vp(beta),
-                                      groups, _vp(w), _vp(b), _vp(out), N, H, W, Cc, Cout, int(circ), _st()))
+    _lib.check(_lib.lib().pf_conv_out(_vp(xp), _lib.dtype_code(xp.dtype), _vp(w), _vp(b), _vp(out), N, H, W, Cc, Cout,
+                                      int(circ), _st()))
     return out
 
 
