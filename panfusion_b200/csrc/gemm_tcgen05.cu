@@ -26,17 +26,21 @@ __host__ __device__ constexpr int gemm_smem_bytes(int block_n, int stages) {
 // [128 rows][32 cols] (64-byte rows, SWIZZLE_64B) and written with TMA tile stores (fully coalesced, rows >= M
 // clipped by the hardware); a 16-bit residual tile is TMA-prefetched into the same staging buffer at kernel start,
 // so it arrives under the main loop instead of as per-thread scattered loads in the epilogue.
-template <int BLOCK_N, int STAGES, bool BF16, bool EPI_TMA>
+// PAIR: launched as clusters of 2 CTAs that issue ONE tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own
+// 128 A rows and only HALF of the B (weight) tile, so the operand bytes pulled from L2 per FLOP drop by ~28 % — the big
+// convolutions are L2->SM bandwidth bound at 128 x 160 tiles.
+template <int BLOCK_N, int STAGES, bool BF16, bool EPI_TMA, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  const GemmKernelParams p) {
   constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
-  constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+  constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * GEMM_BLOCK_K * 2;  // per CTA
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int STAGING_BYTES = EPI_TMA ? GEMM_BLOCK_M * BLOCK_N * 2 : 0;
   constexpr int SUB_BYTES = GEMM_BLOCK_M * 64;  // one [128][32] 16-bit sub-tile
   constexpr int TMEM_COLS = gemm_tmem_cols(BLOCK_N);
+  static_assert(!(PAIR && EPI_TMA), "the CTA-pair variant uses the direct epilogue");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA M=128 needs N%16==0, N<=256");
   static_assert(!EPI_TMA || BLOCK_N % 32 == 0, "staged epilogue works on 32-column sub-tiles");
 
@@ -55,9 +59,11 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = p.N / BLOCK_N;
-  const int n_tile = blockIdx.x % n_tiles;  // n fastest: concurrent CTAs share the A tile through L2
-  const int m_tile = blockIdx.x / n_tiles;
-  const int m0 = m_tile * GEMM_BLOCK_M;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs of the pair)
+  const int tile = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int n_tile = tile % n_tiles;  // n fastest: concurrent CTAs share the A tile through L2
+  const int m_tile = tile / n_tiles;
+  const int m0 = m_tile * (PAIR ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M) + int(rank) * GEMM_BLOCK_M;
   const int n0 = n_tile * BLOCK_N;
 
   if (warp == 0 && lane == 0) {
@@ -73,11 +79,17 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_2sm(tmem_ptr_smem, TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // barrier inits + TMEM allocation visible to the peer CTA
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -96,17 +108,41 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         const int tap = kb / p.kb_per_tap;
         const int kk = kb - tap * p.kb_per_tap;
         uint8_t* sa = smem + s * STAGE_BYTES;
-        tma_load_2d(sa, &tmA, &full_bar[s], kk * GEMM_BLOCK_K, m0 + p.tap_off[tap]);
-        tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], kb * GEMM_BLOCK_K, n0);
+        if constexpr (PAIR) {
+          // the leader arms its barrier with the bytes of BOTH CTAs; each CTA loads its A rows and its half of B
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+          tma_load_2d_2sm(sa, &tmA, &full_bar[s], kk * GEMM_BLOCK_K, m0 + p.tap_off[tap]);
+          tma_load_2d_2sm(sa + A_BYTES, &tmB, &full_bar[s], kb * GEMM_BLOCK_K, n0 + int(rank) * (BLOCK_N / 2));
+        } else {
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[s], kk * GEMM_BLOCK_K, m0 + p.tap_off[tap]);
+          tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], kb * GEMM_BLOCK_K, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
+    if constexpr (PAIR) {
+      if (lane == 0 && rank == 0) {
+        constexpr uint32_t idesc2 = make_idesc_f16(BF16 ? 1 : 0, 2 * GEMM_BLOCK_M, BLOCK_N, 0, 0);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          const int s = kb % STAGES;
+          mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(sa, 16, 1024, 2);
+          const uint64_t bdesc = make_smem_desc(sa + A_BYTES, 16, 1024, 2);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
+            umma_f16_2sm(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc2, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[s]);  // frees the slot in BOTH CTAs
+        }
+        umma_commit_2sm(tmem_full_bar);  // accumulators (128 rows in each CTA's TMEM) complete
+      }
+    } else if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(BF16 ? 1 : 0, GEMM_BLOCK_M, BLOCK_N, 0, 0);
       for (int kb = 0; kb < p.num_kb; ++kb) {
         const int s = kb % STAGES;
@@ -358,10 +394,12 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_before();
   }
 
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer may still be reading this CTA's smem / TMEM through the pair MMA
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -400,7 +438,7 @@ static int launch_gemm(const pf_gemm_args* a, const GemmKernelParams& kp, cudaSt
   const int m_tiles = (a->M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int grid = m_tiles * (a->N / BLOCK_N);
   if (a->dtype == PF_BF16) {
-    auto kern = gemm_taps_kernel<BLOCK_N, STAGES, true, EPI_TMA>;
+    auto kern = gemm_taps_kernel<BLOCK_N, STAGES, true, EPI_TMA, false>;
     static bool attr_set = false;
     if (!attr_set) {
       int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM),
@@ -410,7 +448,7 @@ static int launch_gemm(const pf_gemm_args* a, const GemmKernelParams& kp, cudaSt
     }
     kern<<<grid, GEMM_THREADS, SMEM, st>>>(tmA, tmB, tmC, tmR, kp);
   } else {
-    auto kern = gemm_taps_kernel<BLOCK_N, STAGES, false, EPI_TMA>;
+    auto kern = gemm_taps_kernel<BLOCK_N, STAGES, false, EPI_TMA, false>;
     static bool attr_set = false;
     if (!attr_set) {
       int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM),
@@ -421,6 +459,57 @@ static int launch_gemm(const pf_gemm_args* a, const GemmKernelParams& kp, cudaSt
     kern<<<grid, GEMM_THREADS, SMEM, st>>>(tmA, tmB, tmC, tmR, kp);
   }
   PF_CHECK_LAUNCH("gemm_taps_kernel");
+  return PF_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_gemm_pair(const pf_gemm_args* a, const GemmKernelParams& kp, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  int rc;
+  {
+    uint64_t dims[2] = {(uint64_t)a->Kc, (uint64_t)a->a_rows};
+    uint64_t str[1] = {(uint64_t)a->a_ld * 2};
+    uint32_t box[2] = {GEMM_BLOCK_K, GEMM_BLOCK_M};
+    if ((rc = make_tmap(&tmA, a->dtype, 2, a->A, dims, str, box, 128))) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->Kc * a->num_taps, (uint64_t)a->N};
+    uint64_t str[1] = {(uint64_t)a->b_ld * 2};
+    uint32_t box[2] = {GEMM_BLOCK_K, (uint32_t)BLOCK_N / 2};  // each CTA of the pair stages half of the weight tile
+    if ((rc = make_tmap(&tmB, a->dtype, 2, a->B, dims, str, box, 128))) return rc;
+  }
+  constexpr int SMEM = STAGES * (GEMM_BLOCK_M * GEMM_BLOCK_K * 2 + (BLOCK_N / 2) * GEMM_BLOCK_K * 2) + 128 + BLOCK_N * 4;
+  const int m_pairs = (a->M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * m_pairs * (a->N / BLOCK_N));
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (a->dtype == PF_BF16) {
+    auto kern = gemm_taps_kernel<BLOCK_N, STAGES, true, false, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM), "gemm pair attr"))) return rc;
+      attr_set = true;
+    }
+    if ((rc = check_cuda(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA, tmA, kp), "cudaLaunchKernelEx(gemm pair)"))) return rc;
+  } else {
+    auto kern = gemm_taps_kernel<BLOCK_N, STAGES, false, false, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM), "gemm pair attr"))) return rc;
+      attr_set = true;
+    }
+    if ((rc = check_cuda(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA, tmA, kp), "cudaLaunchKernelEx(gemm pair)"))) return rc;
+  }
+  PF_CHECK_LAUNCH("gemm_taps_kernel(pair)");
   return PF_OK;
 }
 
@@ -504,9 +593,18 @@ extern "C" int pf_gemm_taps(const pf_gemm_args* a, void* stream) {
   // PF_GEMM_SCHED=persistent|tile forces one of them (debugging / A-B timing only).
   static const char* force = getenv("PF_GEMM_SCHED");
   const int m_tiles_ = (a->M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
-  bool persistent = epi_tma && (long long)m_tiles_ * (a->N / bn) >= 2 * 148;
+  bool persistent = (epi_tma || a->act == PF_ACT_GEGLU) && (long long)m_tiles_ * (a->N / bn) >= 2 * 148;
   if (force) persistent = force[0] == 'p';
   if (persistent) return launch_gemm_persistent(a, kp, bn, epi_tma, st);
+  // CTA pairs (cta_group::2, M = 256) for the long-K direct-epilogue GEMMs = the 3x3 convolutions
+  static const char* pair_env = getenv("PF_GEMM_PAIR");
+  bool pair = !epi_tma && a->act != PF_ACT_GEGLU && a->num_taps * a->Kc >= 1024 && (bn == 160 || bn == 256) &&
+              (long long)m_tiles_ * (a->N / bn) >= 148;
+  if (pair_env) pair = pair && pair_env[0] != '0';
+  if (pair) {
+    if (bn == 160) return launch_gemm_pair<160, 4>(a, kp, st);
+    return launch_gemm_pair<256, 3>(a, kp, st);
+  }
   if (epi_tma) {
     switch (bn) {
       case 64: return launch_gemm<64, 4, true>(a, kp, st);

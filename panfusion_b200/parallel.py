@@ -31,6 +31,52 @@ def pick_layout(world: int, b: int, m: int) -> tuple[int, int]:
     return batch_shards, view_shards
 
 
+class GraphSegments:
+    """One denoise step as [graph, collective, graph, collective, ..., graph].
+
+    NCCL collectives are not captured: every time the forward reaches one (`collective(fn)`), the CUDA graph under
+    capture is closed, `fn` runs eagerly on the same stream and is remembered, and a new capture begins (same memory
+    pool, so buffers keep their addresses). `replay()` walks the list. At the break points the panorama side stream
+    has always been joined (EPPA and the output gather run on the main stream), so ending the capture is legal.
+    """
+
+    def __init__(self, pool=None):
+        self.items = []  # CUDAGraph | callable
+        self.pool = pool if pool is not None else torch.cuda.graph_pool_handle()
+        self.stream = torch.cuda.Stream()
+        self._cur = None
+
+    def _begin(self):
+        self._cur = torch.cuda.CUDAGraph()
+        self._cur.capture_begin(pool=self.pool)
+
+    def _end(self):
+        self._cur.capture_end()
+        self.items.append(self._cur)
+        self._cur = None
+
+    def capture(self, body) -> None:
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self._begin()
+            body()
+            self._end()
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+    def collective(self, fn):
+        self._end()
+        fn()
+        self.items.append(fn)
+        self._begin()
+
+    def replay(self) -> None:
+        for it in self.items:
+            if isinstance(it, torch.cuda.CUDAGraph):
+                it.replay()
+            else:
+                it()
+
+
 class ViewParallel:
     def __init__(self, group=None, batch_shards: Optional[int] = None, view_shards: Optional[int] = None):
         self.group = group if group is not None else dist.group.WORLD
@@ -38,6 +84,13 @@ class ViewParallel:
         self.rank = dist.get_rank(self.group)
         self.batch_shards, self.view_shards = batch_shards, view_shards
         self._view_groups = None
+        self.segments: Optional[GraphSegments] = None  # set by the sampler while it captures a step
+
+    def _run(self, fn) -> None:
+        if self.segments is not None:
+            self.segments.collective(fn)
+        else:
+            fn()
 
     def configure(self, b: int, m: int) -> None:
         if self.batch_shards is None or self.view_shards is None:
@@ -66,7 +119,8 @@ class ViewParallel:
             return x
         bl, L, C = x.shape
         out = torch.empty((self.view_shards * bl, L, C), dtype=x.dtype, device=x.device)  # concat along dim 0
-        dist.all_gather_into_tensor(out, x.contiguous(), group=self.view_group)
+        xc, grp = x.contiguous(), self.view_group
+        self._run(lambda: dist.all_gather_into_tensor(out, xc, group=grp))
         out = out.reshape(self.view_shards, bl, L, C)
         if bl == 1:
             return out.reshape(1, self.view_shards * L, C)
@@ -77,13 +131,21 @@ class ViewParallel:
         bl, ml = b // self.batch_shards, m // self.view_shards
         pano_all = torch.empty((self.world * pano_loc.shape[0], *pano_loc.shape[1:]), dtype=pano_loc.dtype,
                                device=pano_loc.device)
-        dist.all_gather_into_tensor(pano_all, pano_loc.contiguous(), group=self.group)
+        pc, grp = pano_loc.contiguous(), self.group
+        s_all, sc = None, None
+        if sample_loc is not None:
+            sc = sample_loc.contiguous()
+            s_all = torch.empty((self.world * sc.shape[0], *sc.shape[1:]), dtype=sc.dtype, device=sc.device)
+
+        def both():
+            dist.all_gather_into_tensor(pano_all, pc, group=grp)
+            if s_all is not None:
+                dist.all_gather_into_tensor(s_all, sc, group=grp)
+
+        self._run(both)
         pano = pano_all.reshape(self.batch_shards, self.view_shards, *pano_loc.shape)[:, 0].reshape(b, *pano_loc.shape[1:])
         sample = None
         if sample_loc is not None:
-            s_all = torch.empty((self.world * sample_loc.shape[0], *sample_loc.shape[1:]), dtype=sample_loc.dtype,
-                                device=sample_loc.device)
-            dist.all_gather_into_tensor(s_all, sample_loc.contiguous(), group=self.group)
             tail = sample_loc.shape[2:]
             s = s_all.reshape(self.batch_shards, self.view_shards, bl, ml, *tail)
             sample = s.permute(0, 2, 1, 3, *range(4, 4 + len(tail))).reshape(b, m, *tail)

@@ -181,12 +181,23 @@ class PanFusionSampler:
             torch.cuda.synchronize()
             st["latents"].copy_(snap["latents"])
             st["pano"].copy_(snap["pano"])
-            g = torch.cuda.CUDAGraph()
             if self._pool is None:
                 self._pool = torch.cuda.graph_pool_handle()
+            par = getattr(self.mv_base_model, "_par", None)
             l0 = ops.LAUNCHES
-            with torch.cuda.graph(g, pool=self._pool):
-                self._step_body(st, cameras)
+            if par is not None:
+                # sharded step: NCCL collectives stay OUTSIDE the graphs (parallel.GraphSegments)
+                from .parallel import GraphSegments
+                g = GraphSegments(self._pool)
+                par.segments = g
+                try:
+                    g.capture(lambda: self._step_body(st, cameras))
+                finally:
+                    par.segments = None
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=self._pool):
+                    self._step_body(st, cameras)
             self.launches_per_step = ops.LAUNCHES - l0  # kernels of ours inside one replayed step
             self._graphs[key] = g
             st["latents"].copy_(snap["latents"])

@@ -37,7 +37,16 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    modes = [m == "1" for m in os.environ.get("MGPU_GRAPH_MODES", "0,1").split(",")]
+    logf = open(Path(__file__).resolve().parent.parent / "gpurun_out" / f"mgpu_rank{rank}.log", "w")
+
+    def log(msg):
+        logf.write(msg + "\n")
+        logf.flush()
+
+    log("init")
     dist.init_process_group("nccl", device_id=dev)
+    log("nccl up")
     views = 8
     g = torch.Generator().manual_seed(0)
     import numpy as np
@@ -49,13 +58,16 @@ def main():
     pano_prompt = torch.cat([null, text]).to(dev)
     prompt = torch.cat([null.repeat(1, views, 1, 1), text.repeat(1, views, 1, 1)]).to(dev)
     ok = True
-    for graph in (False, True):
+    for graph in modes:
         outs = []
         for parallel in (False, True):
+            log(f"build graph={graph} parallel={parallel}")
             model = build(dev, parallel)
             s = PanFusionSampler(model, use_cuda_graph=graph)
+            log("denoise")
             outs.append(s.denoise(lat, pano, prompt, pano_prompt, cams, num_steps=5, rotate_back=False))
             torch.cuda.synchronize()
+            log("done, barrier")
             dist.barrier()
         d_lat = (outs[0][0] - outs[1][0]).abs().max().item()
         d_pano = (outs[0][1] - outs[1][1]).abs().max().item()

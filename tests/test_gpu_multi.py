@@ -1,0 +1,22 @@
+"""-m gpu (needs >= 2 GPUs, skipped otherwise): CFG/view-sharded step == single-GPU step (scripts/mgpu_check.py under
+torchrun, NCCL)."""
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_matches_single(world):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world), str(ROOT / "scripts" / "mgpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MISMATCH" not in r.stdout
