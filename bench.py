@@ -238,6 +238,13 @@ def run_b200(args):
     e2e_sps = args.steps / (ms_e2e / 1e3)
 
     out = None
+    if world > 1:
+        from panfusion_b200.parallel import pick_layout
+        bsh, vsh = pick_layout(world, 2, wl["m"])
+        parallelism = (f"{bsh} CFG shards x {vsh} view shards (one process per GPU; pano branch once per CFG shard; "
+                       f"{'one K|V all-gather per EPPA block + ' if vsh > 1 else ''}one eps all-gather per step, NCCL)")
+    else:
+        parallelism = "single GPU"
     if rank == 0:
         flops = FLOPS_PER_STEP[args.workload]
         ach = steps_per_s * flops / 1e12 / world
@@ -247,7 +254,7 @@ def run_b200(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl["desc"], "views": wl["m"], "cfg_batch": 2, "pano_latent": list(wl["pano_hw"]),
                        "view_latent": list(wl["pers_hw"]), "weights": "random-init SD-2 architecture (seeded)",
-                       "parallelism": f"views sharded {world}-way" if world > 1 else "single GPU",
+                       "parallelism": parallelism,
                        "cuda_graph": not args.no_graph,
                        "l2": "working set (3.4 GB weights + activations per step) exceeds the 126 MB L2; no flush needed"},
             "clocks": clk.summary(),

@@ -18,6 +18,17 @@ namespace pf {
 constexpr int FA_BLOCK_M = 128;
 constexpr int FA_BLOCK_N = 64;
 constexpr int FA_THREADS = 192;
+// Measured on B200 (scripts/fmha_micro.py, 16x5x4096x4096 d64): MUFU-only + cvt packing 668 TFLOP/s; moving every
+// 4th exponential to the FMA pipe and the bf16 packing to the ALU: 615 TFLOP/s (issue slots, not the XU pipe, are
+// the binding constraint at 3 CTAs/SM). Both tricks are kept switchable for the next round's re-tuning.
+#ifndef PF_FA_POLY_EXP
+#define PF_FA_POLY_EXP 0
+#endif
+#ifndef PF_FA_ALU_PACK
+#define PF_FA_ALU_PACK 0
+#endif
+constexpr bool FA_POLY_EXP = PF_FA_POLY_EXP != 0;
+constexpr bool FA_ALU_PACK = PF_FA_ALU_PACK != 0;
 
 struct FmhaParams {
   int B, H, Lq, Lk;
@@ -294,9 +305,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int e = 0; e < FA_BLOCK_N; e += 2) {
         const float p0 = fast_exp2(fmaf(sv[e], sc, -m_used));
         const float a1 = fmaf(sv[e + 1], sc, -m_used);
-        const float p1 = ((e >> 1) & 1) ? poly_exp2(a1) : fast_exp2(a1);  // every 4th element off the MUFU
+        const float p1 = (FA_POLY_EXP && ((e >> 1) & 1)) ? poly_exp2(a1) : fast_exp2(a1);
         ps[(e >> 1) & 3] += p0 + p1;
-        pk[e >> 1] = pack_prob<BF16>(p0, p1);
+        pk[e >> 1] = FA_ALU_PACK ? pack_prob<BF16>(p0, p1) : pack2<BF16>(p0, p1);
       }
       l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
       if (j > 0 && !o_waited) {

@@ -540,7 +540,10 @@ extern "C" int pf_gemm_taps(const pf_gemm_args* a, void* stream) {
   PF_CHECK_ARG(!a->residual || a->res_dtype == PF_F32 || a->res_dtype == a->dtype,
                "pf_gemm_taps: res_dtype must be f32 or dtype");
   PF_CHECK_ARG(a->act >= PF_ACT_NONE && a->act <= PF_ACT_GEGLU, "pf_gemm_taps: unknown act %d", a->act);
-  int bn = a->block_n ? a->block_n : pf_gemm_pick_block_n(a->N, a->act);
+  // block_n: low 16 bits = tile width (0 = auto); bits 16.. = schedule override (0 auto, 1 one-tile-per-CTA,
+  // 2 persistent, 3 CTA pair) — written by scripts/tune_gemm.py into gemm_tuning.json, never needed by callers
+  const int sched_req = a->block_n >> 16;
+  int bn = (a->block_n & 0xffff) ? (a->block_n & 0xffff) : pf_gemm_pick_block_n(a->N, a->act);
   PF_CHECK_ARG(bn == 64 || bn == 128 || bn == 160 || bn == 256, "pf_gemm_taps: unsupported block_n %d (N=%d)", bn, a->N);
   PF_CHECK_ARG(a->N % bn == 0, "pf_gemm_taps: N=%d not a multiple of block_n=%d", a->N, bn);
   const int n_out = a->act == PF_ACT_GEGLU ? a->N / 2 : a->N;
@@ -595,12 +598,14 @@ extern "C" int pf_gemm_taps(const pf_gemm_args* a, void* stream) {
   const int m_tiles_ = (a->M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   bool persistent = (epi_tma || a->act == PF_ACT_GEGLU) && (long long)m_tiles_ * (a->N / bn) >= 2 * 148;
   if (force) persistent = force[0] == 'p';
-  if (persistent) return launch_gemm_persistent(a, kp, bn, epi_tma, st);
+  if (sched_req) persistent = sched_req == 2;
+  if (persistent && (bn != 256 || !epi_tma)) return launch_gemm_persistent(a, kp, bn, epi_tma && bn != 256, st);
   // CTA pairs (cta_group::2, M = 256) for the long-K direct-epilogue GEMMs = the 3x3 convolutions
   static const char* pair_env = getenv("PF_GEMM_PAIR");
   bool pair = !epi_tma && a->act != PF_ACT_GEGLU && a->num_taps * a->Kc >= 1024 && (bn == 160 || bn == 256) &&
               (long long)m_tiles_ * (a->N / bn) >= 148;
   if (pair_env) pair = pair && pair_env[0] != '0';
+  if (sched_req) pair = sched_req == 3 && !epi_tma && a->act != PF_ACT_GEGLU && (bn == 160 || bn == 256);
   if (pair) {
     if (bn == 160) return launch_gemm_pair<160, 4>(a, kp, st);
     return launch_gemm_pair<256, 3>(a, kp, st);

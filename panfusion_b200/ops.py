@@ -38,7 +38,7 @@ def _load_tuning() -> None:
     from pathlib import Path
     f = Path(__file__).with_name("gemm_tuning.json")
     if f.exists():
-        for k, v in json.loads(f.read_text()).get("block_n", {}).items():
+        for k, v in json.loads(f.read_text()).get("choice", {}).items():
             _TUNED[tuple(int(x) for x in k.split(","))] = int(v)
 
 
@@ -69,8 +69,11 @@ def gemm_taps(A: Tensor, B: Tensor, out: Tensor, *, M: int, Kc: int, taps: Seque
     a.M, a.N, a.Kc, a.num_taps = int(M), B.shape[0], int(Kc), len(taps)
     for i, t in enumerate(taps):
         a.tap_off[i] = int(t)
-    if not block_n and act != PF_ACT_GEGLU:
-        block_n = _TUNED.get((int(M), B.shape[0], int(Kc), len(taps)), 0)
+    if block_n == -1:  # heuristic only (tuner baseline)
+        block_n = 0
+    elif not block_n and act != PF_ACT_GEGLU:
+        block_n = _TUNED.get((int(M), B.shape[0], int(Kc), len(taps), int(image_map is not None),
+                              int(residual is not None)), 0)  # tile width | schedule << 16
     a.block_n = int(block_n)
     if GEMM_LOG is not None:
         GEMM_LOG.append((int(M), B.shape[0], int(Kc), len(taps), int(act), image_map is not None,

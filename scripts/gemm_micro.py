@@ -11,13 +11,15 @@ M, N, Kc, ntaps = (int(v) for v in sys.argv[1:5])
 bn = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 act = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 has_res = int(sys.argv[7]) if len(sys.argv) > 7 else 0
+mapped = int(sys.argv[8]) if len(sys.argv) > 8 else 0
 dev = torch.device("cuda:0")
 A = torch.randn(M + 4096, Kc, device=dev).bfloat16()
 B = (torch.randn(N, Kc * ntaps, device=dev) * 0.02).bfloat16()
 n_out = N // 2 if act == 3 else N
 out = torch.empty(M, n_out, dtype=torch.bfloat16, device=dev)
 res = torch.randn(M, n_out, device=dev).bfloat16() if has_res else None
-fn = lambda: ops.gemm_taps(A, B, out, M=M, Kc=Kc, taps=list(range(ntaps)), residual=res, act=act, block_n=bn)
+fn = lambda: ops.gemm_taps(A, B, out, M=M, Kc=Kc, taps=list(range(ntaps)), residual=res, act=act, block_n=bn,
+                           image_map=(1, M, 0, 0, 1, M) if mapped else None)
 for _ in range(3):
     fn()
 torch.cuda.synchronize()

@@ -50,34 +50,58 @@ def main():
         out = torch.empty(M, N, dtype=torch.float32 if out_f32 else dt, device=dev)
         res = torch.randn(M, N, device=dev).to(dt) if has_res else None
         taps = list(range(ntaps))
+        imap = None
+        if mapped:  # a plausible halo-dropping map: one image of M rows, everything valid (timing only)
+            imap = (1, M, 0, 0, 1, M)
         times = {}
+        epi_tma = (not mapped) and (not out_f32)
         for bn in (64, 128, 160, 256):
             if N % bn:
                 continue
-            fn = lambda: ops.gemm_taps(A, B, out, M=M, Kc=Kc, taps=taps, residual=res, act=act, block_n=bn)
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            a, b = ev(), ev()
-            a.record()
-            for _ in range(10):
-                fn()
-            b.record()
-            torch.cuda.synchronize()
-            times[bn] = a.elapsed_time(b) / 10 * 1e3  # us
-        default = ops.pick_block_n(N)
+            for sched in (1, 2, 3):
+                if sched == 3 and (epi_tma or bn not in (160, 256)):
+                    continue
+                if sched == 2 and bn == 256 and epi_tma:
+                    continue
+                code = bn | (sched << 16)
+                fn = lambda: ops.gemm_taps(A, B, out, M=M, Kc=Kc, taps=taps, residual=res, act=act, block_n=code,
+                                           image_map=imap)
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                a, b = ev(), ev()
+                a.record()
+                for _ in range(10):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                times[code] = a.elapsed_time(b) / 10 * 1e3  # us
+        # what the built-in heuristic picks
+        fn = lambda: ops.gemm_taps(A, B, out, M=M, Kc=Kc, taps=taps, residual=res, act=act, block_n=-1, image_map=imap)
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(10):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t_default = a.elapsed_time(b) / 10 * 1e3
         best = min(times, key=times.get)
-        if times[best] < 0.97 * times[default]:
-            table[f"{M},{N},{Kc},{ntaps}"] = best
-        total_before += times[default] * count
-        total_after += times[best] * count
+        if times[best] < 0.97 * t_default:
+            table[f"{M},{N},{Kc},{ntaps},{int(mapped)},{int(has_res)}"] = best
+        total_before += t_default * count
+        total_after += min(times[best], t_default) * count
         fl = 2.0 * M * N * Kc * ntaps
-        results.append(dict(M=M, N=N, Kc=Kc, taps=ntaps, count=count, us=times, best=best,
+        results.append(dict(M=M, N=N, Kc=Kc, taps=ntaps, mapped=mapped, res=has_res, count=count,
+                            us={f"{k & 0xffff}/s{k >> 16}": round(v, 1) for k, v in times.items()},
+                            default_us=round(t_default, 1), best=f"{best & 0xffff}/s{best >> 16}",
                             tflops_best=round(fl / times[best] / 1e6, 1)))
         del A, B, out, res
     print(f"sum over a step: default {total_before / 1e3:.2f} ms -> tuned {total_after / 1e3:.2f} ms")
     out_path.parent.mkdir(exist_ok=True)
-    out_path.write_text(json.dumps(dict(block_n=table, detail=results, default_ms=total_before / 1e3,
+    out_path.write_text(json.dumps(dict(choice=table, detail=results, default_ms=total_before / 1e3,
                                         tuned_ms=total_after / 1e3), indent=1))
     print(f"wrote {out_path} ({len(table)} overrides)")
 
