@@ -334,11 +334,24 @@ def micro_rooflines(dev, pk):
 # ------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle (a port of the reference algorithm) on the host cores
 # ------------------------------------------------------------------------------------------------------
+_ORACLE_MODEL = None
+
+
+def _oracle_model():
+    """SD-2-size oracle model, built once (seeded default init of 2 x 866 M parameters takes ~half a minute)."""
+    global _ORACLE_MODEL
+    if _ORACLE_MODEL is None:
+        from oracle import mvgen as om, synth, unet as ou
+        torch.set_num_threads(os.cpu_count())
+        _ORACLE_MODEL = synth.build_model(om.MultiViewBaseModel, ou.SD2_CONFIG, seed=0)
+    return _ORACLE_MODEL
+
+
 def _oracle_step_time(workload, n_steps=1):
-    from oracle import mvgen as om, sampler as osamp, synth, unet as ou
+    from oracle import sampler as osamp
     wl = WORKLOADS[workload]
     torch.set_num_threads(os.cpu_count())
-    model = synth.build_model(om.MultiViewBaseModel, ou.SD2_CONFIG, seed=0)
+    model = _oracle_model()
     g = torch.Generator().manual_seed(0)
     m = wl["m"]
     cams = osamp.horizon_cameras(m)
@@ -383,7 +396,8 @@ def run_reference(args):
         sample_wl, scale = "c1", FLOPS_PER_STEP[args.workload] / FLOPS_PER_STEP["c1"]
         sample = (f"each step = one oracle step of the 2-view config, scaled by algorithmic FLOPs x{scale:.2f} "
                   f"(a full step is ~{est_full:.0f} s on {cores} threads)")
-    n_timed = max(1, min(args.steps, int(240 / max(t_first * (scale if sample_wl != 'c1' else 1.0), 1e-3))))
+    per_step_est = est_full if sample_wl == args.workload else t_first
+    n_timed = max(1, min(args.steps, int(240 / max(per_step_est, 1e-3))))
     for _ in range(min(args.warmup, 1)):
         _oracle_step_time(sample_wl)
     t0 = time.perf_counter()

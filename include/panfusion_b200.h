@@ -98,9 +98,16 @@ typedef struct pf_gemm_args {
   int32_t res_dtype;
   int32_t act;
   int32_t map_mode, Hm, Wm, i0, j0, Hout, Wout;
+  /* split-K (long-K, few-tile problems: the 8x8 / 16x16 level convolutions): k_splits > 1 partitions the K-slabs over
+   * k_splits CTAs per tile; partial accumulators go to splitk_ws (fp32, k_splits * M * N elements, caller-owned) and
+   * a second kernel reduces them in a fixed order and applies the epilogue. 0 / 1 = off. */
+  int32_t k_splits;
+  float* splitk_ws;
 } pf_gemm_args;
 
 int pf_gemm_taps(const pf_gemm_args* args, void* stream);
+/* suggested k_splits for this problem (1 = do not split); only M, N, Kc, num_taps, act, map_mode, dtypes are read */
+int pf_gemm_splitk_plan(const pf_gemm_args* args);
 /* block_n the auto-tuner would pick for this N (used by the host-side weight packer for GEGLU) */
 int pf_gemm_pick_block_n(int N, int act);
 

@@ -35,6 +35,7 @@ class GemmArgs(C.Structure):
         ("act", C.c_int32),
         ("map_mode", C.c_int32), ("Hm", C.c_int32), ("Wm", C.c_int32), ("i0", C.c_int32), ("j0", C.c_int32),
         ("Hout", C.c_int32), ("Wout", C.c_int32),
+        ("k_splits", C.c_int32), ("splitk_ws", C.c_void_p),
     ]
 
 
@@ -73,7 +74,7 @@ def lib() -> C.CDLL:
 EXPORTS = [
     "pf_last_error", "pf_version", "pf_check_device",
     "pf_e2p", "pf_p2e",
-    "pf_gemm_taps", "pf_gemm_pick_block_n",
+    "pf_gemm_taps", "pf_gemm_pick_block_n", "pf_gemm_splitk_plan",
     "pf_fmha_fwd", "pf_bias_tile_flags",
     "pf_groupnorm_ws_floats", "pf_groupnorm_stats", "pf_conv_prep", "pf_layernorm",
     "pf_conv_in", "pf_conv_out", "pf_copy2d", "pf_timestep_embed", "pf_cfg_ddim_step", "pf_cfg_ddim_step_dev",

@@ -22,6 +22,8 @@ struct GemmKernelParams {
   int res_f32;
   int act;
   int map_mode, Hm, Wm, i0, j0, Hout, Wout;
+  int k_splits;     // > 1: blockIdx.y = split index, raw fp32 partials go to ws
+  float* ws;        // [k_splits][M][N]
 };
 
 __host__ __device__ constexpr int gemm_stage_bytes(int block_n) {

@@ -65,6 +65,10 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int m_tile = tile / n_tiles;
   const int m0 = m_tile * (PAIR ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M) + int(rank) * GEMM_BLOCK_M;
   const int n0 = n_tile * BLOCK_N;
+  // split-K: this CTA owns K-slabs [kb_begin, kb_end)
+  const int split = (!PAIR && p.k_splits > 1) ? int(blockIdx.y) : 0;
+  const int kb_begin = (p.k_splits > 1) ? (int)((long long)split * p.num_kb / p.k_splits) : 0;
+  const int kb_end = (p.k_splits > 1) ? (int)((long long)(split + 1) * p.num_kb / p.k_splits) : p.num_kb;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -104,9 +108,9 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_2d(staging + sub * SUB_BYTES, &tmR, res_full_bar, n0 + sub * 32, m0);
         }
       }
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int s = (kb - kb_begin) % STAGES;
+        const uint32_t ph = ((kb - kb_begin) / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         const int tap = kb / p.kb_per_tap;
         const int kk = kb - tap * p.kb_per_tap;
@@ -144,9 +148,9 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     } else if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(BF16 ? 1 : 0, GEMM_BLOCK_M, BLOCK_N, 0, 0);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int s = (kb - kb_begin) % STAGES;
+        const uint32_t ph = ((kb - kb_begin) / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
@@ -155,7 +159,7 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
           // +32 B per UMMA_K step inside the 128 B swizzle row => +2 in the (addr >> 4) field
-          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
       }
@@ -188,7 +192,25 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     named_bar_sync(1, 128);
 
-    if constexpr (EPI_TMA) {
+    if (p.k_splits > 1) {
+      // split-K partial: raw fp32 accumulators, M-space rows (the reduce kernel applies row map + epilogue)
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      float* wrow = p.ws + ((long long)split * p.M + m) * p.N + n0;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr_row + c, v);
+        tmem_ld_wait();
+        if (m < p.M) {
+          float4* dst = reinterpret_cast<float4*>(wrow + c);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                                 __uint_as_float(v[4 * e + 3]));
+        }
+      }
+    } else if constexpr (EPI_TMA) {
       if (!valid) group = 0;  // rows past M are computed (and clipped by the TMA store): keep their table reads in bounds
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
@@ -403,6 +425,80 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// split-K reduce: fixed-order sum of the k_splits partials, then the same epilogue as the in-kernel one
+// (bias, per-image row bias, activation, residual, halo-dropping row map). thread <-> (M-space row, 8 columns)
+template <bool BF16>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmKernelParams p) {
+  const int vecs = p.N / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)p.M * vecs) return;
+  const int m = int(idx / vecs), c = int(idx % vecs) * 8;
+  bool valid = true;
+  long long orow = m;
+  int group = 0;
+  if (p.map_mode == 1) {
+    const int hw = p.Hm * p.Wm;
+    const int img = m / hw;
+    const int r = m - img * hw;
+    const int i = r / p.Wm;
+    const int j = r - i * p.Wm;
+    valid = i >= p.i0 && i < p.i0 + p.Hout && j >= p.j0 && j < p.j0 + p.Wout;
+    orow = ((long long)img * p.Hout + (i - p.i0)) * p.Wout + (j - p.j0);
+    group = img;
+  } else if (p.rowbias) {
+    group = m / p.rows_per_group;
+  }
+  if (!valid) return;
+  float o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.f;
+  for (int sp = 0; sp < p.k_splits; ++sp) {
+    const float4* w4 = reinterpret_cast<const float4*>(p.ws + ((long long)sp * p.M + m) * p.N + c);
+    const float4 a = __ldcs(w4), b = __ldcs(w4 + 1);
+    o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+    o[4] += b.x; o[5] += b.y; o[6] += b.z; o[7] += b.w;
+  }
+  if (p.bias) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] += __ldg(p.bias + c + e);
+  }
+  if (p.rowbias) {
+    const float* rb = p.rowbias + (long long)group * p.rowbias_ld + c;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] += __ldg(rb + e);
+  }
+  if (p.act == PF_ACT_SILU) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = silu_f(o[e]);
+  } else if (p.act == PF_ACT_GELU) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = gelu_erf_f(o[e]);
+  }
+  if (p.residual) {
+    if (p.res_f32) {
+      const float4* r4 = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + orow * p.res_ld + c);
+      const float4 a = r4[0], b = r4[1];
+      o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+      o[4] += b.x; o[5] += b.y; o[6] += b.z; o[7] += b.w;
+    } else {
+      const uint4 t = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.residual) + orow * p.res_ld + c);
+      float2 f;
+      f = unpack2<BF16>(t.x); o[0] += f.x; o[1] += f.y;
+      f = unpack2<BF16>(t.y); o[2] += f.x; o[3] += f.y;
+      f = unpack2<BF16>(t.z); o[4] += f.x; o[5] += f.y;
+      f = unpack2<BF16>(t.w); o[6] += f.x; o[7] += f.y;
+    }
+  }
+  if (p.out_f32) {
+    float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.out_ld + c);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+  } else {
+    *reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + orow * p.out_ld + c) =
+        make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]), pack2<BF16>(o[4], o[5]), pack2<BF16>(o[6], o[7]));
+  }
+}
+
 template <int BLOCK_N, int STAGES, bool EPI_TMA>
 static int launch_gemm(const pf_gemm_args* a, const GemmKernelParams& kp, cudaStream_t st) {
   CUtensorMap tmA, tmB, tmC, tmR;
@@ -436,7 +532,7 @@ static int launch_gemm(const pf_gemm_args* a, const GemmKernelParams& kp, cudaSt
   }
   constexpr int SMEM = gemm_smem_bytes(BLOCK_N, STAGES) + (EPI_TMA ? GEMM_BLOCK_M * BLOCK_N * 2 : 0);
   const int m_tiles = (a->M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
-  const int grid = m_tiles * (a->N / BLOCK_N);
+  const dim3 grid(m_tiles * (a->N / BLOCK_N), kp.k_splits > 1 ? kp.k_splits : 1);
   if (a->dtype == PF_BF16) {
     auto kern = gemm_taps_kernel<BLOCK_N, STAGES, true, EPI_TMA, false>;
     static bool attr_set = false;
@@ -523,6 +619,20 @@ extern "C" int pf_gemm_pick_block_n(int N, int act) {
   return 0;
 }
 
+extern "C" int pf_gemm_splitk_plan(const pf_gemm_args* a) {
+  if (!a || a->act == PF_ACT_GEGLU || a->M <= 0 || a->N <= 0 || a->Kc <= 0) return 1;
+  const int bn = pf_gemm_pick_block_n(a->N, a->act);
+  if (!bn) return 1;
+  const long long tiles = (long long)((a->M + 127) / 128) * (a->N / bn);
+  const int num_kb = a->Kc / 64 * a->num_taps;
+  if (tiles >= 148 || num_kb < 32) return 1;        // enough CTAs already, or K too short to amortise the reduce
+  int s = (int)((2 * 148 + tiles - 1) / tiles);       // aim for ~2 CTAs per SM
+  const int max_by_k = num_kb / 8;                    // >= 8 K-slabs per split
+  if (s > max_by_k) s = max_by_k;
+  if (s > 16) s = 16;
+  return s < 2 ? 1 : s;
+}
+
 extern "C" int pf_gemm_taps(const pf_gemm_args* a, void* stream) {
   using namespace pf;
   PF_CHECK_ARG(a != nullptr, "pf_gemm_taps: null args");
@@ -583,7 +693,26 @@ extern "C" int pf_gemm_taps(const pf_gemm_args* a, void* stream) {
   kp.j0 = a->j0;
   kp.Hout = a->Hout;
   kp.Wout = a->Wout;
+  kp.k_splits = a->k_splits > 1 ? a->k_splits : 1;
+  kp.ws = a->splitk_ws;
+  PF_CHECK_ARG(kp.k_splits == 1 || (a->splitk_ws && a->act != PF_ACT_GEGLU && kp.k_splits <= kp.num_kb),
+               "pf_gemm_taps: split-K needs a workspace, no GEGLU and k_splits <= K-slabs");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (kp.k_splits > 1) {
+    int rc;
+    switch (bn) {
+      case 64: rc = launch_gemm<64, 4, false>(a, kp, st); break;
+      case 128: rc = launch_gemm<128, 3, false>(a, kp, st); break;
+      case 160: rc = launch_gemm<160, 3, false>(a, kp, st); break;
+      default: rc = launch_gemm<256, 2, false>(a, kp, st); break;
+    }
+    if (rc) return rc;
+    const long long total = (long long)a->M * (a->N / 8);
+    if (a->dtype == PF_BF16) splitk_reduce_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(kp);
+    else splitk_reduce_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(kp);
+    PF_CHECK_LAUNCH("splitk_reduce_kernel");
+    return PF_OK;
+  }
   // staged TMA-store epilogue: plain row map, 16-bit output, 16-bit (or no) residual, no GEGLU
   const bool epi_tma = a->map_mode == 0 && a->out_dtype == a->dtype && a->act != PF_ACT_GEGLU &&
                        (!a->residual || a->res_dtype == a->dtype) && bn != 256 &&

@@ -161,8 +161,9 @@ static int launch_resample(const void* src, void* dst, uint8_t* mask, int B, int
     if (ch_per_stage > 16) ch_per_stage = 16;
     // enough CTAs to fill 148 SMs x 2, but long enough channel runs to amortise the fp64 grid math
     int ch_per_cta = C;
+    // exactly ONE wave of co-resident CTAs (2 per SM): a 3 % overshoot of the 296 slots costs a whole second wave
     const int want_ctas = 148 * 2;
-    int ctas_per_b = (want_ctas + B - 1) / B;
+    int ctas_per_b = want_ctas / B;
     if (ctas_per_b < 1) ctas_per_b = 1;
     ch_per_cta = (C + ctas_per_b - 1) / ctas_per_b;
     ch_per_cta = ((ch_per_cta + ch_per_stage - 1) / ch_per_stage) * ch_per_stage;

@@ -30,6 +30,10 @@ def _st():
 
 # per-shape tile choice measured on B200 by scripts/tune_gemm.py: (M, N, Kc, taps) -> block_n
 GEMM_LOG = None
+# Split-K (pf_gemm_splitk_plan) measured on B200 over the whole step: 33.2 steps/s with, 34.1 without — the few-tile
+# convolutions it targets already overlap with the other UNet branch's stream, so the extra partial-sum traffic is a
+# net loss. Kept (and tested) for single-branch use; opt in with PF_SPLIT_K=1 or k_splits=.
+SPLIT_K = __import__("os").environ.get("PF_SPLIT_K", "0") != "0"
 _TUNED: dict = {}
 
 
@@ -52,7 +56,7 @@ def pick_block_n(n: int, act: int = PF_ACT_NONE) -> int:
 def gemm_taps(A: Tensor, B: Tensor, out: Tensor, *, M: int, Kc: int, taps: Sequence[int] = (0,),
               bias: Optional[Tensor] = None, rowbias: Optional[Tensor] = None, rows_per_group: int = 0,
               residual: Optional[Tensor] = None, act: int = PF_ACT_NONE,
-              image_map: Optional[tuple] = None, block_n: int = 0) -> Tensor:
+              image_map: Optional[tuple] = None, block_n: int = 0, k_splits: Optional[int] = None) -> Tensor:
     """acc = sum_t A[m + taps[t], :Kc] @ B[:, t*Kc:(t+1)*Kc]^T ; see include/panfusion_b200.h (pf_gemm_taps).
 
     A: [a_rows, a_ld] 16-bit, B: [N, len(taps)*Kc] 16-bit packed weight, out: [rows, n_out].
@@ -92,6 +96,14 @@ def gemm_taps(A: Tensor, B: Tensor, out: Tensor, *, M: int, Kc: int, taps: Seque
     if image_map is not None:
         a.map_mode = 1
         a.Hm, a.Wm, a.i0, a.j0, a.Hout, a.Wout = (int(v) for v in image_map)
+    ws = None
+    if k_splits is None:
+        k_splits = _lib.lib().pf_gemm_splitk_plan(C.byref(a)) if SPLIT_K else 1
+    if k_splits > 1:
+        a.block_n = int(block_n) & 0xffff  # split-K runs on the tile-per-CTA schedule
+        ws = torch.empty(k_splits * int(M) * B.shape[0], dtype=torch.float32, device=A.device)
+        a.k_splits, a.splitk_ws = int(k_splits), ws.data_ptr()
+        _count(1)
     _count(1)
     _lib.check(_lib.lib().pf_gemm_taps(C.byref(a), _st()))
     return out

@@ -107,3 +107,29 @@ def test_bad_args_raise(cuda_device):
     out = torch.zeros(128, 64, dtype=torch.float32, device=cuda_device)
     with pytest.raises(ValueError):
         ops.gemm_taps(A, B, out, M=128, Kc=72)  # Kc not a multiple of 64
+
+
+@pytest.mark.parametrize("k_splits", [None, 3, 9])
+def test_conv3x3_split_k(cuda_device, k_splits):
+    """Long-K / few-tile convolution (the 8x8-level shapes): split-K partials + fixed-order reduce == plain path."""
+    from panfusion_b200 import ops
+    from panfusion_b200.packing import pack_conv3x3
+    n, H, W, Cin, Cout = 4, 8, 8, 640, 320
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(n, Cin, H, W, generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).bfloat16()
+    b = torch.randn(Cout, generator=g)
+    temb = torch.randn(n, Cout, generator=g)
+    res = torch.randn(n, Cout, H, W, generator=g).bfloat16()
+    ref = (F.conv2d(x.float(), w.float(), b, padding=1) + temb[:, :, None, None] + res.float()).to(cuda_device)
+    Hp, Wp = H + 2, W + 2
+    xp = torch.zeros(n, Hp, Wp, Cin, dtype=torch.bfloat16)
+    xp[:, 1:-1, 1:-1] = x.permute(0, 2, 3, 1)
+    A = xp.reshape(n * Hp * Wp, Cin).to(cuda_device)
+    taps = [(dy - 1) * Wp + (dx - 1) for dy in range(3) for dx in range(3)]
+    out = torch.empty(n * H * W, Cout, dtype=torch.float32, device=cuda_device)
+    ops.gemm_taps(A, pack_conv3x3(w).to(cuda_device), out, M=n * Hp * Wp, Kc=Cin, taps=taps, bias=b.to(cuda_device),
+                  rowbias=temb.to(cuda_device), residual=res.permute(0, 2, 3, 1).reshape(n * H * W, Cout).contiguous().to(cuda_device),
+                  image_map=(Hp, Wp, 1, 1, H, W), k_splits=k_splits)
+    got = out.reshape(n, H, W, Cout).permute(0, 3, 1, 2)
+    torch.testing.assert_close(got, ref, rtol=1e-3, atol=2e-4)
