@@ -47,6 +47,9 @@ def _camera_record(kind: str, fov: float, theta: float, phi: float, h: int, w: i
     return tuple(rec.tolist())
 
 
+_RECORD_CACHE: dict = {}
+
+
 def _scalar(v, i):
     """index_list_or_scalar (utils.py:18-23)."""
     if hasattr(v, "__len__"):
@@ -62,9 +65,15 @@ def camera_records(kind: str, fov_deg, u_deg, v_deg, batch: int, h: int, w: int,
         n, stride = 1, 0
     else:
         n, stride = batch, 1
-    recs = [_camera_record(kind, _scalar(fov_deg, i), _scalar(u_deg, i), _scalar(v_deg, i), int(h), int(w))
-            for i in range(n)]
-    t = torch.tensor(recs, dtype=torch.float64).to(device, non_blocking=True)
+    key = (kind, tuple(_scalar(fov_deg, i) for i in range(n)), tuple(_scalar(u_deg, i) for i in range(n)),
+           tuple(_scalar(v_deg, i) for i in range(n)), int(h), int(w), str(device))
+    t = _RECORD_CACHE.get(key)
+    if t is None:
+        recs = [_camera_record(kind, key[1][i], key[2][i], key[3][i], int(h), int(w)) for i in range(n)]
+        t = torch.tensor(recs, dtype=torch.float64).to(device)
+        if len(_RECORD_CACHE) > 4096:
+            _RECORD_CACHE.clear()
+        _RECORD_CACHE[key] = t  # device-resident: repeated warps with the same rig launch without any host->device copy
     return t, stride
 
 

@@ -70,3 +70,31 @@ def test_fmha_fused_qkv_views_and_batched_bias(cuda_device):
     out = torch.empty(B, L, C, dtype=torch.float16, device=cuda_device)
     ops.fmha(q, k, v, out, heads=H, head_dim=d, scale=d ** -0.5, bias=bias)
     torch.testing.assert_close(out.float(), ref, rtol=1e-3, atol=1e-3)
+
+
+def test_bias_tile_flags_and_sparse_bias_attention(cuda_device):
+    """pf_bias_tile_flags marks 128x64 tiles that are entirely -1; attention with the flag table == without it."""
+    from panfusion_b200 import ops
+    G, Lq, Lk, H, d = 2, 300, 200, 4, 32
+    g = torch.Generator().manual_seed(9)
+    bias = torch.full((G, Lq, Lk), -1.0)
+    bias[0, 10:40, 70:90] = torch.rand(30, 20, generator=g) * 2 - 1      # touches tiles (0, 1)
+    bias[1, 250:300, 0:10] = torch.rand(50, 10, generator=g) * 2 - 1     # touches tiles (1..2, 0)
+    bias = bias.to(cuda_device)
+    flags = ops.bias_tile_flags(bias)
+    assert flags.shape == (G, 3, 4)
+    ref = torch.ones(G, 3, 4, dtype=torch.uint8)
+    ref[0, 0, 1] = 0
+    ref[1, 1, 0] = 0
+    ref[1, 2, 0] = 0
+    assert torch.equal(flags.cpu(), ref)
+    C = H * d
+    q = torch.randn(G, Lq, C, generator=g).half().to(cuda_device)
+    k = torch.randn(G, Lk, C, generator=g).half().to(cuda_device)
+    v = torch.randn(G, Lk, C, generator=g).half().to(cuda_device)
+    o1 = torch.empty(G, Lq, C, dtype=torch.float16, device=cuda_device)
+    o2 = torch.empty_like(o1)
+    ops.fmha(q, k, v, o1, heads=H, head_dim=d, scale=d ** -0.5, bias=bias)
+    ops.fmha(q, k, v, o2, heads=H, head_dim=d, scale=d ** -0.5, bias=bias, bias_flags=flags)
+    torch.testing.assert_close(o1.float(), o2.float(), rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(o2.float(), _ref(q, k, v, H, d, d ** -0.5, bias), rtol=1e-3, atol=1e-3)
