@@ -109,6 +109,15 @@ class UNetPack:
         f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
         self.conv_in_w, self.conv_in_b = f32(unet.conv_in.weight), f32(unet.conv_in.bias)
         self.conv_out_w, self.conv_out_b = f32(unet.conv_out.weight), f32(unet.conv_out.bias)
+        # conv_out (C -> 4) on the tensor cores: output channels zero-padded to one 64-wide tap-GEMM tile
+        co = unet.conv_out.weight.shape[0]
+        wpad = torch.zeros((64, *unet.conv_out.weight.shape[1:]), dtype=unet.conv_out.weight.dtype,
+                           device=unet.conv_out.weight.device)
+        wpad[:co] = unet.conv_out.weight.detach()
+        self.conv_out_packed = pack_conv3x3(wpad).to(dev, dt).contiguous()
+        bpad = torch.zeros(64, dtype=torch.float32, device=dev)
+        bpad[:co] = self.conv_out_b
+        self.conv_out_bpad, self.conv_out_c = bpad, co
         self.norm_out = _Norm(unet.conv_norm_out, dev)
         te = unet.time_embedding
         self.t_dim = te.linear_1.weight.shape[1]
@@ -213,7 +222,13 @@ class Branch:
         stats = ops.groupnorm_stats(x.t, x.N, x.H, x.W, p.groups, p.norm_out.eps, 0)  # un-padded (MVGenModel.py:288)
         xp = ops.conv_prep(x.t, x.N, x.H, x.W, stats=stats, gamma=p.norm_out.g, beta=p.norm_out.b, groups=p.groups,
                            act=ops.PF_ACT_SILU, circ=c, halo=1)
-        return ops.conv_out(xp, x.N, x.H, x.W, p.conv_out_w, p.conv_out_b, c)
+        # 3x3 conv as 9 taps (the 64-column tile holds the 4 real output channels + zero padding), fp32 out
+        We = x.W + 2 * c
+        Hp, Wp = x.H + 2, We + 2
+        o = torch.empty((x.N * x.H * x.W, 64), dtype=torch.float32, device=x.t.device)
+        ops.gemm_taps(xp, p.conv_out_packed, o, M=x.N * Hp * Wp, Kc=x.C, taps=taps3x3(Wp), bias=p.conv_out_bpad,
+                      image_map=(Hp, Wp, 1, 1 + c, x.H, x.W), block_n=64)
+        return o[:, :p.conv_out_c].reshape(x.N, x.H, x.W, p.conv_out_c).permute(0, 3, 1, 2).contiguous()
 
     def resnet(self, x: Img, r: _Resnet) -> Img:
         """ResnetBlock2D; panorama: pad_pano(2) -> block -> unpad_pano(2) (MVGenModel.py:110-115)."""
