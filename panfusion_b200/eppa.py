@@ -145,7 +145,7 @@ class WarpAttn(nn.Module):
         self._packed = None
 
     # ---- token-level forward used by MultiViewBaseModel -----------------------------------------
-    def forward_tokens(self, pers: Img, equi: Img, cam_key: tuple, par=None) -> tuple[Img, Img]:
+    def forward_tokens(self, pers: Img, equi: Img, cam_key: tuple, par=None, side=None, keep=None) -> tuple[Img, Img]:
         """pers: (b*m_loc) images of ph x pw, equi: b images of eh x ew; cam_key = CameraTables.camera_key(cameras)
         of ALL b*m cameras. `par` (parallel.ViewParallel) marks pers as this rank's slice of the views: the K|V of
         the other view shards arrive through one all-gather, everything else is local."""
@@ -195,10 +195,22 @@ class WarpAttn(nn.Module):
                               block_n=w["ff1_bn"])
             return ops.gemm_taps(f, w["ff2"].w, new(rows, C), M=rows, Kc=4 * C, bias=w["ff2"].b, residual=x1)
 
+        # The two directions only share their inputs: direction 1 (few pano tokens, under-filled launches) runs on the
+        # panorama branch's side stream, concurrently with direction 2 on the caller's stream. Its result is consumed
+        # by the panorama branch on that same stream, so no join is needed here; the shared inputs produced on the
+        # caller's stream are parked in `keep` until the branches next join.
+        main = torch.cuda.current_stream()
+        two = side is not None and side is not main
+        if two:
+            side.wait_event(main.record_event())
+            if keep is not None:
+                keep.extend([qkv_p, qkv_e, k_all, v_all, equi.t])
         # direction 1 (modules.py:44-48): pano pixels query every view's pixels
-        o1 = torch.empty((b, E, C), dtype=dt, device=dev)
-        ops.fmha(qkv_e[..., :C], k_all, v_all, o1, heads=heads, head_dim=d, scale=scale, bias=bias1, bias_flags=flags1)
-        equi_out = finish(o1.reshape(Te, C), equi.t, Te)
+        with torch.cuda.stream(side if two else main):
+            o1 = torch.empty((b, E, C), dtype=dt, device=dev)
+            ops.fmha(qkv_e[..., :C], k_all, v_all, o1, heads=heads, head_dim=d, scale=scale, bias=bias1,
+                     bias_flags=flags1)
+            equi_out = finish(o1.reshape(Te, C), equi.t, Te)
         # direction 2 (modules.py:51-55): view pixels query the pano; reads the INPUT features
         o2 = torch.empty((b, m_loc * P, C), dtype=dt, device=dev)
         ops.fmha(qkv_p[..., :C], qkv_e[..., C:2 * C], qkv_e[..., 2 * C:], o2, heads=heads, head_dim=d, scale=scale,

@@ -20,6 +20,9 @@ from .engine import Branch, Img, UNetPack
 from .eppa import CameraTables, WarpAttn
 
 
+_EPPA_SPLIT = __import__("os").environ.get("PF_EPPA_SPLIT", "1") != "0"  # A/B switch (scripts only)
+
+
 class MultiViewBaseModel(nn.Module):
     def __init__(self, unet, pano_unet, pers_cn=None, pano_cn=None, pano_pad=True, compute_dtype=torch.bfloat16,
                  overlap_branches=True):
@@ -124,9 +127,13 @@ class MultiViewBaseModel(nn.Module):
 
         def fuse(block, h, p):
             join()
-            h, p = block.forward_tokens(h, p, cam_key, par)
-            keep.append(p.t)
-            fork()
+            # direction 1 of the fusion continues on the side stream and feeds the panorama branch there; direction 2
+            # stays on the main stream: after the block the two streams are already forked again
+            split = two and _EPPA_SPLIT
+            h, p = block.forward_tokens(h, p, cam_key, par, side=side if split else None, keep=keep)
+            if not split:
+                keep.append(p.t)
+                fork()
             return h, p
 
         fork()
