@@ -26,7 +26,8 @@ sys.path.insert(0, str(ROOT))
 
 import torch  # noqa: E402
 
-FLOPS_PER_STEP = {"c2": 17.733e12, "c1": 3.669e12}  # SURVEY.md App. C (algorithmic, 2*MAC, un-padded widths)
+# SURVEY.md App. C (algorithmic, 2*MAC, un-padded widths); c1 here = 2 views WITH CFG (2x the survey's no-CFG C1)
+FLOPS_PER_STEP = {"c2": 17.733e12, "c1": 3.669e12, "c4": 64.084e12, "c5": 19.060e12}
 METRIC = "denoise-steps/sec (512x1024 pano + 8x512^2 views, 50-step DDIM)"
 WORKLOADS = {
     # name: (views m, pano latent HxW, pers latent hxw, CFG)
@@ -34,7 +35,28 @@ WORKLOADS = {
                desc="512x1024 pano + 8x512x512 views, CFG batch 2, 50-step DDIM (BASELINE configs[1])"),
     "c1": dict(m=2, pano_hw=(64, 128), pers_hw=(64, 64), cfg=True,
                desc="512x1024 pano + 2x512x512 views, CFG batch 2 (reduced-view parity config)"),
+    "c4": dict(m=20, pano_hw=(128, 256), pers_hw=(64, 64), cfg=True, cameras="icosahedron",
+               desc="1024x2048 pano + 20x512x512 icosahedron views, CFG batch 2 (BASELINE configs[3])"),
+    "c5": dict(m=8, pano_hw=(64, 128), pers_hw=(64, 64), cfg=True, layout_cond=True,
+               desc="512x1024 pano + 8x512x512 views + panorama ControlNet (layout condition), CFG batch 2 "
+                    "(BASELINE configs[4])"),
 }
+
+
+def icosahedron_cameras():
+    """20 face-centre cameras of a regular icosahedron (utils/pano.py:34-71): two rings of 5 at +-phi_a (offset by
+    half a step) and two at +-phi_b; degrees."""
+    import numpy as np
+    r_circ, r_in, r_mid = np.sin(2 * np.pi / 5), np.sqrt(3) / 12 * (3 + np.sqrt(5)), np.cos(np.pi / 5)
+    step = 2 * np.pi / 5
+    phi_a = np.pi / 2 - np.arccos(r_in / r_circ)
+    phi_b = phi_a - 2 * np.arccos(r_in / r_mid)
+    theta, phi = [], []
+    for ring, (p, off) in enumerate(((phi_a, step / 2), (phi_b, step / 2), (-phi_b, 0.0), (-phi_a, 0.0))):
+        for k in range(5):
+            theta.append(-np.pi + off + k * step)
+            phi.append(p)
+    return np.rad2deg(np.array(theta)), np.rad2deg(np.array(phi))
 
 
 def peaks():
@@ -100,14 +122,22 @@ def synthetic_inputs(wl, ctx_dim, device, sampler, seed=0):
     import numpy as np
     m = wl["m"]
     g = torch.Generator().manual_seed(seed)
-    theta = np.rad2deg(np.linspace(0, 2 * np.pi, m, endpoint=False))  # utils/pano.py:28-31
-    cams = dict(FoV=torch.full((1, m), 90.0), theta=torch.tensor(theta, dtype=torch.float32)[None], phi=torch.zeros(1, m))
+    if wl.get("cameras") == "icosahedron":
+        theta, phi = icosahedron_cameras()
+    else:
+        theta = np.rad2deg(np.linspace(0, 2 * np.pi, m, endpoint=False))  # utils/pano.py:28-31
+        phi = np.zeros(m)
+    cams = dict(FoV=torch.full((1, m), 90.0), theta=torch.tensor(theta, dtype=torch.float32)[None],
+                phi=torch.tensor(phi, dtype=torch.float32)[None])
     pano = torch.randn(1, 1, 4, *wl["pano_hw"], generator=g)
     text = torch.randn(1, 1, 77, ctx_dim, generator=g)
     null = torch.randn(1, 1, 77, ctx_dim, generator=g)
     pano_prompt = torch.cat([null, text])                                              # PanFusion.py:135-138
     prompt = torch.cat([null.repeat(1, m, 1, 1), text.repeat(1, m, 1, 1)])             # copy_pano_prompt
-    return dict(cams=cams, pano=pano, prompt=prompt, pano_prompt=pano_prompt)
+    out = dict(cams=cams, pano=pano, prompt=prompt, pano_prompt=pano_prompt)
+    if wl.get("layout_cond"):  # layout image at pixel resolution (8x the latent), values in [0, 1]
+        out["pano_layout_cond"] = torch.rand(1, 1, 3, wl["pano_hw"][0] * 8, wl["pano_hw"][1] * 8, generator=g)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -135,7 +165,8 @@ def run_b200(args):
     unet = sd2_unet.build_synthetic(seed=1, device=dev)
     pano_unet = sd2_unet.build_synthetic(seed=2, device=dev)
     torch.manual_seed(3)
-    model = MultiViewBaseModel(unet, pano_unet, compute_dtype=dtype).to(dev).eval()
+    pano_cn = sd2_unet.build_synthetic_controlnet(seed=5, device=dev) if wl.get("layout_cond") else None
+    model = MultiViewBaseModel(unet, pano_unet, pano_cn=pano_cn, compute_dtype=dtype).to(dev).eval()
     g = torch.Generator(device=dev).manual_seed(4)
     with torch.no_grad():
         for name, p in sorted(model.named_parameters()):
@@ -158,7 +189,8 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     n_sched = sampler.diff_timestep
-    sampler.start(lat, pano, prompt, pano_prompt, inp["cams"])
+    cond = inp["pano_layout_cond"].to(dev) if "pano_layout_cond" in inp else None
+    sampler.start(lat, pano, prompt, pano_prompt, inp["cams"], pano_layout_cond=cond)
     if args.profile_one_step:
         # ncu --profile-from-start off: tables/weights warmed by 4 eager steps, then exactly one step is profiled
         sampler.use_cuda_graph = False

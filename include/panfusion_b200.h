@@ -179,9 +179,11 @@ int pf_layernorm(const void* x, int ldx, void* out, int ldo, int dtype, int T, i
                  const float* gamma, const float* beta, float eps, void* stream);
 
 /* conv_in (MVGenModel.py:85-91): NCHW fp32 latent [N,Cin,H,W] -> tokens [N*H*W, Cout] 16-bit; 3x3 pad 1;
- * circ != 0 wraps columns (== pad_pano(1) -> conv -> unpad_pano(1)). w fp32 [Cout,Cin,3,3], bias fp32 [Cout]. */
+ * circ != 0 wraps columns (== pad_pano(1) -> conv -> unpad_pano(1)). w fp32 [Cout,Cin,3,3], bias fp32 [Cout].
+ * act = PF_ACT_SILU applies SiLU to the result: the first convolution of the ControlNet conditioning embedding on the
+ * 3-channel layout image (diffusers ControlNetConditioningEmbedding [3P], consumed at MVGenModel.py:66-83). */
 int pf_conv_in(const float* x, const float* w, const float* bias, void* out, int dtype, int N, int Cin, int H, int W,
-               int Cout, int circ, void* stream);
+               int Cout, int circ, int act, void* stream);
 
 /* conv_out (MVGenModel.py:279-295) over the PREPARED tensor: xp = pf_conv_prep(conv_norm_out statistics of the
  * un-padded tensor as the reference does at :288, SiLU, circ, halo = 1) of shape [N, H+2, W+2*circ+2, C] 16-bit

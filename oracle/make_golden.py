@@ -97,6 +97,24 @@ def main():
         return _report(f"MultiViewBaseModel {tag}", [rs, rp_], [os_, op_])
 
     worst = max(worst, mv(ounet.TINY_CONFIG, (16, 32), (16, 16), "tiny"))
+
+    # 5. layout-conditioned step (BASELINE config 5): the reference's residual wiring (MVGenModel.py:62-83,154-170,
+    # 200-203) executed as-is around the duck-typed ControlNet restatement (oracle/controlnet.py, [3P])
+    def mv_cn(config, pano_hw, pers_hw, tag, pers):
+        model_r = synth.build_model_cn(ref.MultiViewBaseModel, config, seed=0, pers=pers)
+        model_o = synth.build_model_cn(om.MultiViewBaseModel, config, seed=0, pers=pers)
+        model_o.load_state_dict(model_r.state_dict())
+        inp = synth.step_inputs(2, pano_hw, pers_hw, config["cross_attention_dim"], seed=0)
+        inp.update(synth.layout_conds(1, 2, pano_hw, pers_hw, seed=5, pers=pers))
+        rs, rp_ = model_r(**inp)
+        os_, op_ = model_o(**inp)
+        base_s, base_p = model_r(**{**inp, "pano_layout_cond": None, "pers_layout_cond": None})
+        print(f"  [{tag}] effect of the layout condition: {(rs - base_s).abs().max():.3e} / {(rp_ - base_p).abs().max():.3e}")
+        np.savez_compressed(OUT / f"mvgen_{tag}.npz", sample=rs.numpy(), pano_sample=rp_.numpy())
+        return _report(f"MultiViewBaseModel {tag}", [rs, rp_], [os_, op_])
+
+    worst = max(worst, mv_cn(ounet.TINY_CONFIG, (16, 32), (16, 16), "tiny_cn", False))
+    worst = max(worst, mv_cn(ounet.TINY_CONFIG, (16, 32), (16, 16), "tiny_cn2", True))
     if args.full:
         worst = max(worst, mv(ounet.SD2_CONFIG, (64, 128), (64, 64), "c1"))
     print(f"worst oracle-vs-reference deviation: {worst:.3e}")

@@ -69,11 +69,13 @@ def rotate_latent(pano_latent, cameras, degree=90.0):
 
 
 def forward_cls_free(model, latents, pano_latent, timestep, prompt_embd, pano_prompt_embd, cameras,
-                     guidance_scale=9.0):
-    """PanFusion.py:100-112: duplicate inputs (uncond first, text second), one forward, combine."""
-    dup = lambda t: torch.cat([t] * 2)
+                     guidance_scale=9.0, pers_layout_cond=None, pano_layout_cond=None):
+    """PanFusion.py:100-112: duplicate inputs (uncond first, text second; layout conditions too,
+    PanoGenerator.py:240-251), one forward, combine."""
+    dup = lambda t: torch.cat([t] * 2) if t is not None else None
     cams2 = {k: dup(v) for k, v in cameras.items()}
-    eps, pano_eps = model(dup(latents), dup(pano_latent), dup(timestep), prompt_embd, pano_prompt_embd, cams2)
+    eps, pano_eps = model(dup(latents), dup(pano_latent), dup(timestep), prompt_embd, pano_prompt_embd, cams2,
+                          dup(pers_layout_cond), dup(pano_layout_cond))
     def combine(e):
         u, c = e.chunk(2)
         return u + guidance_scale * (c - u)
@@ -82,7 +84,8 @@ def forward_cls_free(model, latents, pano_latent, timestep, prompt_embd, pano_pr
 
 @torch.no_grad()
 def denoise_steps(model, latents, pano_latent, prompt_embd, pano_prompt_embd, cameras, num_steps,
-                  diff_timestep=50, guidance_scale=9.0, rot_diff=90.0, start_step=0):
+                  diff_timestep=50, guidance_scale=9.0, rot_diff=90.0, start_step=0, pers_layout_cond=None,
+                  pano_layout_cond=None):
     """`num_steps` iterations of the hot loop PanFusion.py:146-162. prompt_embd / pano_prompt_embd are the CFG
     concatenations [null; text] of shape [2, m, 77, C] / [2, 1, 77, C]. Returns (latents, pano_latent, cameras)."""
     sched = DDIM()
@@ -91,8 +94,10 @@ def denoise_steps(model, latents, pano_latent, prompt_embd, pano_prompt_embd, ca
     for t in sched.timesteps[start_step:start_step + num_steps]:
         timestep = torch.cat([t[None, None]] * m, dim=1)
         pano_latent, cameras = rotate_latent(pano_latent, cameras, rot_diff)
+        if pano_layout_cond is not None and rot_diff % 360:  # PanFusion.py:152-153: rolled every step, cumulatively
+            pano_layout_cond = torch.roll(pano_layout_cond, int(rot_diff / 360 * pano_layout_cond.shape[-1]), dims=-1)
         eps, pano_eps = forward_cls_free(model, latents, pano_latent, timestep, prompt_embd, pano_prompt_embd,
-                                         cameras, guidance_scale)
+                                         cameras, guidance_scale, pers_layout_cond, pano_layout_cond)
         latents = sched.step(eps, t, latents)
         pano_latent = sched.step(pano_eps, t, pano_latent)
     return latents, pano_latent, cameras

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import torch
 
-from . import sampler, unet as ounet
+from . import controlnet as ocn, sampler, unet as ounet
 
 
 def randomize_zero_init(model: torch.nn.Module, seed: int = 1234, std: float = 0.02) -> None:
@@ -41,3 +41,25 @@ def build_model(model_cls, config=None, seed: int = 0):
     torch.random.set_rng_state(st)
     randomize_zero_init(model, seed + 3)
     return model
+
+
+def build_model_cn(model_cls, config=None, seed: int = 0, pers: bool = False):
+    """build_model + a panorama ControlNet (and optionally a perspective one; off by default in the reference,
+    PanoGenerator.py:77). The ControlNet encoders are `from_unet` copies of DIFFERENTLY seeded UNets, so using the
+    UNet's weights in place of the ControlNet's shows up in the output."""
+    config = config or ounet.SD2_CONFIG
+    base = build_model(model_cls, config, seed)
+    pano_cn = ocn.build_controlnet(ounet.build_unet(config, seed=seed + 11), seed=seed + 12)
+    pers_cn = ocn.build_controlnet(ounet.build_unet(config, seed=seed + 13), seed=seed + 14) if pers else None
+    model = model_cls(base.unet, base.pano_unet, pers_cn=pers_cn, pano_cn=pano_cn).eval()
+    model.load_state_dict(base.state_dict(), strict=False)  # the EPPA blocks (incl. redrawn zero-init tensors)
+    return model
+
+
+def layout_conds(batch: int, m: int, pano_hw, pers_hw, seed: int = 5, pers: bool = False):
+    """Layout-condition images at 8x the latent resolution (PanFusion.py:152-153 rolls the pano one 256 px/step)."""
+    g = torch.Generator().manual_seed(seed)
+    out = dict(pano_layout_cond=torch.rand(batch, 1, 3, pano_hw[0] * 8, pano_hw[1] * 8, generator=g))
+    if pers:
+        out["pers_layout_cond"] = torch.rand(batch, m, 3, pers_hw[0] * 8, pers_hw[1] * 8, generator=g)
+    return out

@@ -12,7 +12,7 @@ namespace pf {
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-               uint16_t* __restrict__ out, int N, int Cin, int H, int W, int Cout, int circ) {
+               uint16_t* __restrict__ out, int N, int Cin, int H, int W, int Cout, int circ, int act) {
   // weights transposed into shared memory as [Cin*9][Cout] (+bias row): lanes read consecutive output channels
   extern __shared__ float s_w[];
   const int K = Cin * 9;
@@ -67,6 +67,12 @@ conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
         }
       }
       const size_t pix0 = ((size_t)n * H + yy) * W + xq;
+      if (act == PF_ACT_SILU) {
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[pp][e] = silu_f(acc[pp][e]);
+      }
 #pragma unroll
       for (int pp = 0; pp < 4; ++pp)
         *reinterpret_cast<uint4*>(out + (pix0 + pp) * Cout + v * 8) =
@@ -107,6 +113,10 @@ conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
           acc[6] = fmaf(val, w1.z, acc[6]); acc[7] = fmaf(val, w1.w, acc[7]);
         }
       }
+    }
+    if (act == PF_ACT_SILU) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = silu_f(acc[e]);
     }
     *reinterpret_cast<uint4*>(out + (size_t)pix * Cout + v * 8) =
         make_uint4(pack2<BF16>(acc[0], acc[1]), pack2<BF16>(acc[2], acc[3]), pack2<BF16>(acc[4], acc[5]),
@@ -217,11 +227,12 @@ cfg_ddim_kernel(const float* __restrict__ x, const float* __restrict__ eps, floa
 }  // namespace pf
 
 extern "C" int pf_conv_in(const float* x, const float* w, const float* bias, void* out, int dtype, int N, int Cin,
-                          int H, int W, int Cout, int circ, void* stream) {
+                          int H, int W, int Cout, int circ, int act, void* stream) {
   using namespace pf;
   PF_CHECK_ARG(x && w && out, "pf_conv_in: null pointer");
   PF_CHECK_ARG(dtype == PF_BF16 || dtype == PF_F16, "pf_conv_in: 16-bit output dtype required");
   PF_CHECK_ARG(N > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0 && Cout % 8 == 0, "pf_conv_in: bad shape");
+  PF_CHECK_ARG(act == PF_ACT_NONE || act == PF_ACT_SILU, "pf_conv_in: act must be none or silu");
   const long long total = (long long)N * H * ((W & 3) ? W : W / 4) * (Cout / 8);
   long long want = (total + 255) / 256;
   const unsigned blocks = (unsigned)(want < 148 * 4 ? want : 148 * 4);  // persistent-ish: weights staged once per CTA
@@ -232,11 +243,11 @@ extern "C" int pf_conv_in(const float* x, const float* w, const float* bias, voi
   if (dtype == PF_BF16) {
     auto k = conv_in_kernel<true>;
     if ((rc = check_cuda(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv_in attr"))) return rc;
-    k<<<blocks, 256, smem, st>>>(x, w, bias, static_cast<uint16_t*>(out), N, Cin, H, W, Cout, circ);
+    k<<<blocks, 256, smem, st>>>(x, w, bias, static_cast<uint16_t*>(out), N, Cin, H, W, Cout, circ, act);
   } else {
     auto k = conv_in_kernel<false>;
     if ((rc = check_cuda(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv_in attr"))) return rc;
-    k<<<blocks, 256, smem, st>>>(x, w, bias, static_cast<uint16_t*>(out), N, Cin, H, W, Cout, circ);
+    k<<<blocks, 256, smem, st>>>(x, w, bias, static_cast<uint16_t*>(out), N, Cin, H, W, Cout, circ, act);
   }
   PF_CHECK_LAUNCH("conv_in_kernel");
   return PF_OK;

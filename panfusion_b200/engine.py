@@ -103,22 +103,24 @@ class _Transformer:
 class UNetPack:
     """All weights of one UNet, packed for the kernels; built once per (device, dtype)."""
 
-    def __init__(self, unet, dev, dt):
+    def __init__(self, unet, dev, dt, encoder_only: bool = False):
+        """encoder_only: a ControlNet (conv_in, time embedding, down_blocks, mid_block; no decoder / conv_out)."""
         self.dev, self.dt = dev, dt
-        self.groups = int(unet.conv_norm_out.num_groups)
+        self.groups = int(unet.down_blocks[0].resnets[0].norm1.num_groups)
         f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
         self.conv_in_w, self.conv_in_b = f32(unet.conv_in.weight), f32(unet.conv_in.bias)
-        self.conv_out_w, self.conv_out_b = f32(unet.conv_out.weight), f32(unet.conv_out.bias)
-        # conv_out (C -> 4) on the tensor cores: output channels zero-padded to one 64-wide tap-GEMM tile
-        co = unet.conv_out.weight.shape[0]
-        wpad = torch.zeros((64, *unet.conv_out.weight.shape[1:]), dtype=unet.conv_out.weight.dtype,
-                           device=unet.conv_out.weight.device)
-        wpad[:co] = unet.conv_out.weight.detach()
-        self.conv_out_packed = pack_conv3x3(wpad).to(dev, dt).contiguous()
-        bpad = torch.zeros(64, dtype=torch.float32, device=dev)
-        bpad[:co] = self.conv_out_b
-        self.conv_out_bpad, self.conv_out_c = bpad, co
-        self.norm_out = _Norm(unet.conv_norm_out, dev)
+        if not encoder_only:
+            self.conv_out_w, self.conv_out_b = f32(unet.conv_out.weight), f32(unet.conv_out.bias)
+            # conv_out (C -> 4) on the tensor cores: output channels zero-padded to one 64-wide tap-GEMM tile
+            co = unet.conv_out.weight.shape[0]
+            wpad = torch.zeros((64, *unet.conv_out.weight.shape[1:]), dtype=unet.conv_out.weight.dtype,
+                               device=unet.conv_out.weight.device)
+            wpad[:co] = unet.conv_out.weight.detach()
+            self.conv_out_packed = pack_conv3x3(wpad).to(dev, dt).contiguous()
+            bpad = torch.zeros(64, dtype=torch.float32, device=dev)
+            bpad[:co] = self.conv_out_b
+            self.conv_out_bpad, self.conv_out_c = bpad, co
+            self.norm_out = _Norm(unet.conv_norm_out, dev)
         te = unet.time_embedding
         self.t_dim = te.linear_1.weight.shape[1]
         self.te1, self.te2 = _Lin(te.linear_1.weight, te.linear_1.bias, dev, dt), _Lin(te.linear_2.weight, te.linear_2.bias, dev, dt)
@@ -145,7 +147,7 @@ class UNetPack:
                 down=[_Conv3(d.conv, dev, dt) for d in blk.downsamplers] if blk.downsamplers is not None else None))
         self.mid = dict(resnets=[res(r) for r in unet.mid_block.resnets], attns=[tr(t) for t in unet.mid_block.attentions])
         self.up = []
-        for blk in unet.up_blocks:
+        for blk in ([] if encoder_only else unet.up_blocks):
             has_attn = bool(getattr(blk, "has_cross_attention", False))
             self.up.append(dict(
                 resnets=[res(r) for r in blk.resnets],
@@ -209,6 +211,9 @@ class Branch:
         ops.gemm_taps(x, p.kv_all.w, kv, M=n * L, Kc=ctx)
         self.text_kv = kv.reshape(n, L, p.kv_all.n)
         self._text_key = key
+        # the key is the tensor's IDENTITY (address, version): hold the storage so that the address cannot be handed
+        # to a different tensor while this entry is alive
+        self._text_owner = prompt
 
     # ---- blocks ------------------------------------------------------------------------------------
     def conv_in(self, latent: Tensor) -> Img:
@@ -321,3 +326,135 @@ class Branch:
         ops.copy2d(a.t, out[:, :a.C])
         ops.copy2d(b.t, out[:, a.C:])
         return Img(out, a.N, a.H, a.W)
+
+
+# ---- ControlNet (BASELINE config 5) ------------------------------------------------------------------------------
+
+def _pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+class _Conv3Padded:
+    """3x3 conv whose channel counts are zero-padded to multiples of 64 (the tap-GEMM's K-slab / narrowest tile)."""
+
+    def __init__(self, conv, dev, dt):
+        w = conv.weight.detach()
+        self.cout_real, self.cin_real = w.shape[0], w.shape[1]
+        self.cout, self.cin = _pad64(w.shape[0]), _pad64(w.shape[1])
+        wp = torch.zeros((self.cout, self.cin, 3, 3), dtype=w.dtype, device=w.device)
+        wp[:w.shape[0], :w.shape[1]] = w
+        self.w = pack_conv3x3(wp).to(dev, dt).contiguous()
+        self.b = torch.zeros(self.cout, dtype=torch.float32, device=dev)
+        self.b[:w.shape[0]] = conv.bias.detach().to(dev, torch.float32)
+        self.stride = int(conv.stride[0])
+
+
+class ControlNetPack(UNetPack):
+    """Weights of a duck-typed diffusers `ControlNetModel` [3P] (built by the reference with
+    `ControlNetModel.from_unet`, models/pano/PanoGenerator.py:153-157): the UNet-encoder copy + conditioning embedding
+    (3x3 convs 3->16->16->32->32->96->96->256->320, SiLU between, strides 1,1,2,1,2,1,2,1) + one 1x1 conv per skip tensor
+    and one for the mid output."""
+
+    def __init__(self, cn, dev, dt):
+        super().__init__(cn, dev, dt, encoder_only=True)
+        ce = cn.controlnet_cond_embedding
+        w0 = ce.conv_in.weight.detach()
+        c0 = _pad64(w0.shape[0])
+        self.ce_in_w = torch.zeros((c0, *w0.shape[1:]), dtype=torch.float32, device=dev)
+        self.ce_in_w[:w0.shape[0]] = w0.to(dev, torch.float32)
+        self.ce_in_b = torch.zeros(c0, dtype=torch.float32, device=dev)
+        self.ce_in_b[:w0.shape[0]] = ce.conv_in.bias.detach().to(dev, torch.float32)
+        self.ce_blocks = [_Conv3Padded(b, dev, dt) for b in ce.blocks]
+        self.ce_out = _Conv3Padded(ce.conv_out, dev, dt)
+        assert self.ce_out.cout == self.ce_out.cout_real, "conditioning embedding width must be a multiple of 64"
+        self.zero_down = [_Lin(c.weight, c.bias, dev, dt) for c in cn.controlnet_down_blocks]
+        self.zero_mid = _Lin(cn.controlnet_mid_block.weight, cn.controlnet_mid_block.bias, dev, dt)
+
+
+class ControlBranch(Branch):
+    """The ControlNet encoder. The reference hands it the UN-padded latent and calls it as a black box
+    (MVGenModel.py:66-83), so every convolution here is zero-padded even on the panorama (`circular=False`)."""
+
+    def __init__(self, pack: ControlNetPack):
+        super().__init__(pack, circular=False)
+        self._cond_cache: dict = {}
+
+    def _conv3(self, x: Img, c: _Conv3Padded, act: int, residual: Optional[Tensor] = None, prepared=None) -> Img:
+        N, H, W = x.N, x.H, x.W
+        dev = x.t.device
+        if c.stride == 1:
+            a = prepared if prepared is not None else ops.conv_prep(x.t, N, H, W, halo=1)
+            Hp, Wp = H + 2, W + 2
+            out = torch.empty((N * H * W, c.cout), dtype=self.dt, device=dev)
+            ops.gemm_taps(a, c.w, out, M=N * Hp * Wp, Kc=c.cin, taps=taps3x3(Wp), bias=c.b, act=act, residual=residual,
+                          image_map=(Hp, Wp, 1, 1, H, W))
+            return Img(out, N, H, W)
+        a = ops.conv_prep(x.t, N, H, W, phases=4, halo=1)
+        Ho, Wo = H // 2, W // 2
+        Hq, Wq = Ho + 1, Wo + 1
+        PS = N * Hq * Wq
+        taps = [((dy % 2) * 2 + (dx % 2)) * PS + (dy // 2) * Wq + (dx // 2) for dy in range(3) for dx in range(3)]
+        out = torch.empty((N * Ho * Wo, c.cout), dtype=self.dt, device=dev)
+        ops.gemm_taps(a, c.w, out, M=PS, Kc=c.cin, taps=taps, bias=c.b, act=act, image_map=(Hq, Wq, 0, 0, Ho, Wo))
+        return Img(out, N, Ho, Wo)
+
+    def cond_features(self, cond: Tensor, key=None):
+        """controlnet_cond_embedding up to (not including) its last convolution, returned as that convolution's
+        prepared A operand. Depends only on the layout image, which the sampler merely rolls by a quarter turn per
+        step (PanFusion.py:152-153): cached on the identity + version of the caller's tensor, like the text K/V."""
+        key = key if key is not None else (cond.data_ptr(), cond._version, tuple(cond.shape))
+        hit = self._cond_cache.get(key)
+        if hit is not None:
+            return hit[:4]
+        p = self.p
+        n, _, hc, wc = cond.shape
+        x = Img(ops.conv_in(cond.to(torch.float32).contiguous(), p.ce_in_w, p.ce_in_b, self.dt, False,
+                            act=ops.PF_ACT_SILU), n, hc, wc)
+        for blk in p.ce_blocks:
+            x = self._conv3(x, blk, ops.PF_ACT_SILU)
+        # entry keeps `cond` alive: the key is its identity, so its address must not be reused while cached
+        hit = (ops.conv_prep(x.t, x.N, x.H, x.W, halo=1), x.N, x.H, x.W, cond)
+        if len(self._cond_cache) >= 8:
+            self._cond_cache.clear()
+        self._cond_cache[key] = hit
+        return hit[:4]
+
+    def encode(self, latent: Tensor, cond: Tensor, cond_key=None):
+        """-> (12 skip-shaped tensors, mid tensor) BEFORE the zero convs (applied by `add_down` / `add_mid` where the
+        reference adds the residuals). set_timesteps / set_text must have been called."""
+        p = self.p
+        a, n, h, w = self.cond_features(cond, cond_key)
+        x = self.conv_in(latent)
+        assert (n, h, w) == (x.N, x.H, x.W), "layout condition must be 8x the latent resolution"
+        x = self._conv3(x, p.ce_out, ops.PF_ACT_NONE, residual=x.t, prepared=a)  # conv_in(sample) + embedding(cond)
+        res = [x]
+        for blk in p.down:
+            for j, r in enumerate(blk["resnets"]):
+                x = self.resnet(x, r)
+                if blk["attns"] is not None:
+                    x = self.transformer(x, blk["attns"][j])
+                res.append(x)
+            if blk["down"] is not None:
+                for d in blk["down"]:
+                    x = self.downsample(x, d)
+                res.append(x)
+        x = self.resnet(x, p.mid["resnets"][0])
+        for i, t in enumerate(p.mid["attns"]):
+            x = self.transformer(x, t)
+            x = self.resnet(x, p.mid["resnets"][i + 1])
+        return res, x
+
+    def _zero(self, lin: _Lin, r: Img, target: Img) -> Img:
+        T = r.t.shape[0]
+        out = torch.empty((T, lin.n), dtype=self.dt, device=r.t.device)
+        ops.gemm_taps(r.t, lin.w, out, M=T, Kc=lin.k, bias=lin.b, residual=target.t)
+        return Img(out, target.N, target.H, target.W)
+
+    def add_down(self, res: list, skips: list) -> list:
+        """skip_i + controlnet_down_blocks[i](res_i)  (MVGenModel.py:154-170), one GEMM with residual epilogue each."""
+        assert len(res) == len(skips) == len(self.p.zero_down)
+        return [self._zero(z, r, s) for z, r, s in zip(self.p.zero_down, res, skips)]
+
+    def add_mid(self, mid: Img, hidden: Img) -> Img:
+        """hidden + controlnet_mid_block(mid)  (MVGenModel.py:200-203)."""
+        return self._zero(self.p.zero_mid, mid, hidden)

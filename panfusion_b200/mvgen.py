@@ -16,7 +16,7 @@ import torch.nn as nn
 from torch import Tensor
 
 from . import _lib
-from .engine import Branch, Img, UNetPack
+from .engine import Branch, ControlBranch, ControlNetPack, Img, UNetPack
 from .eppa import CameraTables, WarpAttn
 
 
@@ -64,6 +64,9 @@ class MultiViewBaseModel(nn.Module):
         pers = Branch(UNetPack(self.unet, device, dtype), circular=False) if self.unet is not None else None
         pano = Branch(UNetPack(self.pano_unet, device, dtype), circular=bool(self.pano_pad))
         self._branches = (pers, pano, device, dtype)
+        # ControlNets (MVGenModel.py:13-14): optional encoder copies whose outputs are added to the skips / mid output
+        self._cn = (ControlBranch(ControlNetPack(self.pers_cn, device, dtype)) if self.pers_cn is not None and pers else None,
+                    ControlBranch(ControlNetPack(self.pano_cn, device, dtype)) if self.pano_cn is not None else None)
         if self.unet is not None:
             for w in [*self.cp_blocks_encoder, self.cp_blocks_mid, *self.cp_blocks_decoder]:
                 w.invalidate()
@@ -76,9 +79,10 @@ class MultiViewBaseModel(nn.Module):
     @torch.no_grad()
     def forward(self, latents: Optional[Tensor], pano_latent: Tensor, timestep: Tensor, prompt_embd: Optional[Tensor],
                 pano_prompt_embd: Tensor, cameras: Optional[dict], pers_layout_cond=None, pano_layout_cond=None):
-        if (self.pers_cn is not None and pers_layout_cond is not None) or \
-                (self.pano_cn is not None and pano_layout_cond is not None):
-            raise NotImplementedError("ControlNet residuals (MVGenModel.py:62-83) are not on the sm_100a path yet")
+        if self.pers_cn is None or self.unet is None:  # MVGenModel.py:62-65
+            pers_layout_cond = None
+        if self.pano_cn is None:
+            pano_layout_cond = None
         _lib.require_cuda(pano_latent)
         if self._branches is None or self._branches[2] != pano_latent.device:
             self.prepare(pano_latent.device)
@@ -97,6 +101,8 @@ class MultiViewBaseModel(nn.Module):
             latents, timestep, prompt_embd = latents[bsl, vsl], timestep[bsl, vsl], prompt_embd[bsl, vsl]
             pano_latent, pano_prompt_embd = pano_latent[bsl], pano_prompt_embd[bsl]
             cameras = {k: v[bsl] for k, v in cameras.items()}
+            pers_layout_cond = pers_layout_cond[bsl, vsl] if pers_layout_cond is not None else None
+            pano_layout_cond = pano_layout_cond[bsl] if pano_layout_cond is not None else None
         if has_pers:
             b, m = latents.shape[:2]
             cam_key = CameraTables.camera_key({k: v.flatten(0, 1) for k, v in cameras.items()})
@@ -137,6 +143,21 @@ class MultiViewBaseModel(nn.Module):
             return h, p
 
         fork()
+        # ControlNets (MVGenModel.py:66-83): black-box encoder passes on the UN-padded latents; their outputs are only
+        # needed after the encoder, so the panorama one simply runs first on the side stream
+        pers_cn, pano_cn = self._cn
+        pers_cn_out = pano_cn_out = None
+        if pers_layout_cond is not None:
+            pers_cn.set_timesteps(timestep.reshape(-1))
+            pers_cn.set_text(prompt_embd.flatten(0, 1), text_key + ("cn",))
+            pers_cn_out = pers_cn.encode(latents.flatten(0, 1), pers_layout_cond.flatten(0, 1),
+                                         tkey(pers_layout_cond, "pers_cond") if par is None else None)
+        if pano_layout_cond is not None:
+            with torch.cuda.stream(side):
+                pano_cn.set_timesteps(timestep[:, 0] if has_pers else timestep)
+                pano_cn.set_text(pano_prompt_embd.flatten(0, 1), pano_text_key + ("cn",))
+                pano_cn_out = pano_cn.encode(pano_latent.flatten(0, 1), pano_layout_cond.flatten(0, 1),
+                                             tkey(pano_layout_cond, "pano_cond") if par is None else None)
         # conv_in (MVGenModel.py:85-91)
         h = pers.conv_in(latents.flatten(0, 1)) if has_pers else None
         with torch.cuda.stream(side):
@@ -169,6 +190,13 @@ class MultiViewBaseModel(nn.Module):
                 if has_pers:
                     h, p = fuse(self.cp_blocks_encoder[i], h, p)
 
+        # ControlNet residuals join the SKIP tensors only after the whole encoder has run (MVGenModel.py:154-170)
+        if pers_cn_out is not None:
+            skips = pers_cn.add_down(pers_cn_out[0], skips)
+        if pano_cn_out is not None:
+            with torch.cuda.stream(side):
+                pano_skips = pano_cn.add_down(pano_cn_out[0], pano_skips)
+
         # mid (MVGenModel.py:172-207)
         if has_pers:
             h = pers.resnet(h, pers.p.mid["resnets"][0])
@@ -181,6 +209,11 @@ class MultiViewBaseModel(nn.Module):
             with torch.cuda.stream(side):
                 p = pano.transformer(p, pat)
                 p = pano.resnet(p, pano.p.mid["resnets"][i + 1])
+        if pers_cn_out is not None:  # MVGenModel.py:200-203
+            h = pers_cn.add_mid(pers_cn_out[1], h)
+        if pano_cn_out is not None:
+            with torch.cuda.stream(side):
+                p = pano_cn.add_mid(pano_cn_out[1], p)
         if has_pers:
             h, p = fuse(self.cp_blocks_mid, h, p)
 

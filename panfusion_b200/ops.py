@@ -223,14 +223,14 @@ def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, pe: Opt
     return out
 
 
-def conv_in(x: Tensor, w: Tensor, b: Optional[Tensor], dtype: torch.dtype, circ: bool) -> Tensor:
+def conv_in(x: Tensor, w: Tensor, b: Optional[Tensor], dtype: torch.dtype, circ: bool, act: int = PF_ACT_NONE) -> Tensor:
     """x NCHW fp32 -> tokens [N*H*W, Cout]."""
     N, Cin, H, W = x.shape
     Cout = w.shape[0]
     out = torch.empty((N * H * W, Cout), dtype=dtype, device=x.device)
     _count(1)
     _lib.check(_lib.lib().pf_conv_in(_vp(x), _vp(w), _vp(b), _vp(out), _lib.dtype_code(dtype), N, Cin, H, W, Cout,
-                                     int(circ), _st()))
+                                     int(circ), int(act), _st()))
     return out
 
 

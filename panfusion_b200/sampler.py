@@ -83,11 +83,12 @@ class PanFusionSampler:
 
     # ---- PanFusion.py:100-112 -----------------------------------------------------------------------
     @torch.no_grad()
-    def forward_cls_free(self, latents, pano_latent, timestep, prompt_embd, pano_prompt_embd, cameras):
-        dup = lambda t: torch.cat([t] * 2)
+    def forward_cls_free(self, latents, pano_latent, timestep, prompt_embd, pano_prompt_embd, cameras,
+                         pers_layout_cond=None, pano_layout_cond=None):
+        dup = lambda t: torch.cat([t] * 2) if t is not None else None
         cams2 = {k: dup(v) for k, v in cameras.items()}
         eps, pano_eps = self.mv_base_model(dup(latents), dup(pano_latent), dup(timestep), prompt_embd,
-                                           pano_prompt_embd, cams2)
+                                           pano_prompt_embd, cams2, dup(pers_layout_cond), dup(pano_layout_cond))
         comb = lambda e: e[:e.shape[0] // 2] + self.guidance_scale * (e[e.shape[0] // 2:] - e[:e.shape[0] // 2])
         return comb(eps), comb(pano_eps)
 
@@ -98,7 +99,7 @@ class PanFusionSampler:
         dup = lambda t: torch.cat([t] * 2)
         cams2 = {k: dup(v) for k, v in cameras.items()}
         eps, pano_eps = self.mv_base_model(dup(st["latents"]), dup(st["pano"]), dup(st["timestep"]), st["prompt"],
-                                           st["pano_prompt"], cams2)
+                                           st["pano_prompt"], cams2, st.get("pers_cond"), st.get("pano_cond"))
         ops.cfg_ddim_step_dev(st["latents"], eps.contiguous(), st["latents_next"], self.guidance_scale, st["coef"])
         W = st["pano"].shape[-1]
         ops.cfg_ddim_step_dev(st["pano"], pano_eps.contiguous(), st["pano_next"], self.guidance_scale, st["coef"],
@@ -109,9 +110,12 @@ class PanFusionSampler:
     # ---- the hot loop (PanFusion.py:146-164) as start / step / finish ---------------------------------
     @torch.no_grad()
     def start(self, latents: Tensor, pano_latent: Tensor, prompt_embd: Tensor, pano_prompt_embd: Tensor,
-              cameras: dict) -> None:
+              cameras: dict, pers_layout_cond: Optional[Tensor] = None,
+              pano_layout_cond: Optional[Tensor] = None) -> None:
         """Bind static buffers. prompt_embd [2, m, 77, C] / pano_prompt_embd [2, 1, 77, C] are the CFG concatenations
-        [null; text] (PanFusion.py:135-138); cameras: dict of tensors [1, m] (CPU or CUDA)."""
+        [null; text] (PanFusion.py:135-138); cameras: dict of tensors [1, m] (CPU or CUDA). Layout conditions
+        (ControlNet): pano_layout_cond [1, 1, 3, 8H, 8W] is rolled by rot_diff EVERY step like the latent
+        (PanFusion.py:152-153); pers_layout_cond [1, m, 3, 8h, 8w] is passed through unchanged (:103-104)."""
         dev = latents.device
         self.scheduler.set_timesteps(self.diff_timestep)
         m = latents.shape[1]
@@ -127,9 +131,23 @@ class PanFusionSampler:
                   coef=torch.zeros(2, dtype=torch.float32, device=dev),
                   coef_table=coefs.to(dev), ts_table=self.scheduler.timesteps.to(dev, torch.float32))
         st["latents_next"], st["pano_next"] = torch.empty_like(st["latents"]), torch.empty_like(st["pano"])
+        dup = lambda t: torch.cat([t] * 2).contiguous()
+        if pers_layout_cond is not None:
+            st["pers_cond"] = dup(pers_layout_cond.to(dev))
+        self._cond_phases = None
+        if pano_layout_cond is not None:
+            # the rolled conditions repeat with a short period (4 for 90 degrees): keep every phase as its own tensor,
+            # so the ControlNet's conditioning embedding is computed once per phase and cached on the tensor identity
+            Wc = pano_layout_cond.shape[-1]
+            r = int(self.rot_diff / 360 * Wc) % Wc if self.rot_diff % 360 else 0
+            period = Wc // math.gcd(Wc, r) if r else 1
+            if period > 8:
+                raise NotImplementedError(f"layout condition with rot_diff={self.rot_diff}: {period} distinct rolls")
+            self._cond_phases = [dup(torch.roll(pano_layout_cond.to(dev), (k + 1) * r, dims=-1)) for k in range(period)]
         self._st = st
         self._cameras = {k: v.detach().to("cpu", torch.float32) for k, v in cameras.items()}
         self._curr_rot = 0.0
+        self._n_rot = 0
         self._graphs = {}
 
     @torch.no_grad()
@@ -142,6 +160,10 @@ class PanFusionSampler:
             self._cameras["theta"] = (self._cameras["theta"] + self.rot_diff) % 360
         st["timestep"].copy_(st["ts_table"][i].expand_as(st["timestep"]))
         st["coef"].copy_(st["coef_table"][i])
+        if self._cond_phases is not None:
+            self._n_rot = getattr(self, "_n_rot", 0)
+            st["pano_cond"] = self._cond_phases[self._n_rot % len(self._cond_phases)]
+            self._n_rot += 1
         self._run_step(st, self._cameras)
 
     @torch.no_grad()
@@ -157,8 +179,8 @@ class PanFusionSampler:
 
     @torch.no_grad()
     def denoise(self, latents, pano_latent, prompt_embd, pano_prompt_embd, cameras, num_steps=None, start_step=0,
-                rotate_back=True):
-        self.start(latents, pano_latent, prompt_embd, pano_prompt_embd, cameras)
+                rotate_back=True, pers_layout_cond=None, pano_layout_cond=None):
+        self.start(latents, pano_latent, prompt_embd, pano_prompt_embd, cameras, pers_layout_cond, pano_layout_cond)
         for i in range(start_step, start_step + (num_steps or self.diff_timestep)):
             self.step(i)
         lat, pano = self.finish(rotate_back)
@@ -172,7 +194,8 @@ class PanFusionSampler:
             return
         key = (tuple(cameras["theta"].reshape(-1).tolist()), tuple(cameras["phi"].reshape(-1).tolist()),
                tuple(cameras["FoV"].reshape(-1).tolist()), tuple(st["latents"].shape), tuple(st["pano"].shape),
-               st["latents"].data_ptr(), st["pano"].data_ptr(), st["prompt"].data_ptr())
+               st["latents"].data_ptr(), st["pano"].data_ptr(), st["prompt"].data_ptr(),
+               st["pano_cond"].data_ptr() if "pano_cond" in st else 0)
         entry = self._graphs.get(key)
         if entry is None:
             # eager warm-up builds the camera tables / packs weights / sets kernel attributes, then capture

@@ -137,3 +137,53 @@ def build_synthetic(config: dict | None = None, seed: int = 0, device="cpu") -> 
         net = SD2UNetParams(**config)
     torch.random.set_rng_state(gens)
     return net.eval()
+
+
+class SD2ControlNetParams(_Holder):
+    """Parameter tree of diffusers `ControlNetModel.from_unet(unet)` [3P] (models/pano/PanoGenerator.py:153-157):
+    `conv_in`, `time_proj`, `time_embedding`, `down_blocks`, `mid_block` (same attribute tree as the UNet encoder),
+    `controlnet_cond_embedding.{conv_in, blocks[6], conv_out}` (3x3 convs 3->16->16->32->32->96->96->256->C0, strides
+    1,1,2,1,2,1,2,1), `controlnet_down_blocks[12]` and `controlnet_mid_block` (1x1 convs)."""
+
+    def __init__(self, conditioning_embedding_out_channels=(16, 32, 96, 256), **config):
+        super().__init__()
+        enc = SD2UNetParams(**config)
+        self.conv_in, self.time_proj, self.time_embedding = enc.conv_in, enc.time_proj, enc.time_embedding
+        self.down_blocks, self.mid_block = enc.down_blocks, enc.mid_block
+        boc = tuple(conditioning_embedding_out_channels)
+        ce = _Holder()
+        ce.conv_in = nn.Conv2d(3, boc[0], 3, padding=1)
+        ce.blocks = nn.ModuleList()
+        for i in range(len(boc) - 1):
+            ce.blocks.append(nn.Conv2d(boc[i], boc[i], 3, padding=1))
+            ce.blocks.append(nn.Conv2d(boc[i], boc[i + 1], 3, padding=1, stride=2))
+        c0 = enc.conv_in.out_channels
+        ce.conv_out = nn.Conv2d(boc[-1], c0, 3, padding=1)
+        self.controlnet_cond_embedding = ce
+        chans = [c0]
+        for blk in self.down_blocks:
+            chans += [r.out_channels for r in blk.resnets]
+            if blk.downsamplers is not None:
+                chans.append(blk.downsamplers[-1].out_channels)
+        self.controlnet_down_blocks = nn.ModuleList([nn.Conv2d(c, c, 1) for c in chans])
+        cm = self.mid_block.resnets[-1].out_channels
+        self.controlnet_mid_block = nn.Conv2d(cm, cm, 1)
+
+    @property
+    def dtype(self):
+        return self.conv_in.weight.dtype
+
+
+def build_synthetic_controlnet(config: dict | None = None, seed: int = 0, device="cpu") -> SD2ControlNetParams:
+    """Random-init ControlNet of the SD-2 architecture (PyTorch default init under `seed`; the zero-initialised convs of
+    a fresh diffusers ControlNet are drawn like every other conv so that they contribute to the output)."""
+    config = config or SD2_CONFIG
+    dev = torch.device(device)
+    gens = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    if dev.type == "cuda":
+        torch.cuda.manual_seed(seed)
+    with torch.device(dev):
+        net = SD2ControlNetParams(**config)
+    torch.random.set_rng_state(gens)
+    return net.eval()

@@ -96,6 +96,24 @@ def test_conv_in_out(cuda_device, circ):
     torch.testing.assert_close(got.cpu(), ref, rtol=2e-3, atol=3e-3)  # the prepared activations are rounded to fp16
 
 
+@pytest.mark.parametrize("W", [32, 30])  # 4-pixel register-blocked path and the generic one
+def test_conv_in_silu_layout_image(cuda_device, W):
+    """pf_conv_in with act = SiLU on a 3-channel image: first conv of the ControlNet conditioning embedding, output
+    channels zero-padded 16 -> 64 (padded channels must come out exactly 0 = silu(0))."""
+    from panfusion_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    N, H = 2, 24
+    img = torch.rand(N, 3, H, W, generator=g)
+    w, b = torch.randn(16, 3, 3, 3, generator=g) * 0.3, torch.randn(16, generator=g)
+    ref = F.silu(F.conv2d(img, w, b, padding=1))
+    wp, bp = torch.zeros(64, 3, 3, 3), torch.zeros(64)
+    wp[:16], bp[:16] = w, b
+    got = ops.conv_in(img.to(cuda_device), wp.to(cuda_device), bp.to(cuda_device), torch.float16, False,
+                      act=ops.PF_ACT_SILU).float().cpu().reshape(N, H, W, 64).permute(0, 3, 1, 2)
+    torch.testing.assert_close(got[:, :16], ref, rtol=1e-3, atol=1e-3)
+    assert got[:, 16:].abs().max().item() == 0.0
+
+
 def test_timestep_embed_and_copy(cuda_device):
     from panfusion_b200 import ops
     from oracle.unet import Timesteps

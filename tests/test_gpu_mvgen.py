@@ -97,3 +97,125 @@ def test_mvgen_c1_vs_reference_golden(cuda_device, dtype):
     gold = np.load(GOLD / "mvgen_c1.npz")
     _check("MultiViewBaseModel C1 sample", s, torch.from_numpy(gold["sample"]), dtype)
     _check("MultiViewBaseModel C1 pano", p, torch.from_numpy(gold["pano_sample"]), dtype)
+
+
+def _build_cn_pair(cuda_device, config, dtype, pers):
+    from oracle import mvgen as om, synth
+    from panfusion_b200.mvgen import MultiViewBaseModel
+    orc = synth.build_model_cn(om.MultiViewBaseModel, config, seed=0, pers=pers)
+    mine = MultiViewBaseModel(orc.unet, orc.pano_unet, pers_cn=orc.pers_cn, pano_cn=orc.pano_cn, compute_dtype=dtype)
+    mine.load_state_dict(orc.state_dict())
+    mine.prepare(cuda_device, dtype)
+    return orc, mine
+
+
+def _to_dev(inp, dev):
+    return {k: (v.to(dev) if torch.is_tensor(v) else {kk: vv.to(dev) for kk, vv in v.items()}) for k, v in inp.items()}
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("tag,pers", [("tiny_cn", False), ("tiny_cn2", True)])
+def test_mvgen_controlnet_vs_reference_golden(cuda_device, dtype, tag, pers):
+    """BASELINE config 5 (layout-conditioned): golden = the reference's MVGenModel.py executed around the ControlNet
+    restatement; checks the conditioned output AND the ControlNet's own contribution (conditioned - unconditioned),
+    which a wrong residual wiring / zero-conv / conditioning embedding would change."""
+    from oracle import synth, unet as ou
+    cfg = ou.TINY_CONFIG
+    orc, mine = _build_cn_pair(cuda_device, cfg, dtype, pers)
+    inp = synth.step_inputs(2, (16, 32), (16, 16), cfg["cross_attention_dim"], seed=0)
+    inp.update(synth.layout_conds(1, 2, (16, 32), (16, 16), seed=5, pers=pers))
+    gold = np.load(GOLD / f"mvgen_{tag}.npz")
+    base = np.load(GOLD / "mvgen_tiny.npz")
+    cu = _to_dev(inp, cuda_device)
+    s, p = mine(**cu)
+    s2, p2 = mine(**cu)  # second call: cached conditioning features
+    s0, p0 = mine(**{**cu, "pano_layout_cond": None, "pers_layout_cond": None})
+    torch.cuda.synchronize()
+    assert torch.equal(s, s2) and torch.equal(p, p2)
+    _check(f"MultiViewBaseModel {tag} sample", s, torch.from_numpy(gold["sample"]), dtype)
+    _check(f"MultiViewBaseModel {tag} pano", p, torch.from_numpy(gold["pano_sample"]), dtype)
+    _check(f"MultiViewBaseModel {tag} no-cond pano", p0, torch.from_numpy(base["pano_sample"]), dtype)
+    # the ControlNet's contribution itself, relative to ITS magnitude
+    dref = torch.from_numpy(gold["pano_sample"] - base["pano_sample"])
+    dgot = (p - p0).float().cpu()
+    mx = (dgot - dref).abs().max().item() / dref.abs().max().item()
+    print(f"[parity] {tag} {dtype}: ControlNet contribution err {mx:.3e} of its max {dref.abs().max().item():.3e}")
+    assert mx < (0.05 if dtype == torch.float16 else 0.25)
+    # changing the condition image must change the output (cache is keyed on identity + version)
+    cu["pano_layout_cond"].mul_(0.5)
+    _, p3 = mine(**cu)
+    assert (p3 - p).abs().max().item() > 1e-3
+
+
+def test_controlnet_pano_only_branch(cuda_device):
+    """unet=None with a panorama ControlNet (PanoOnly ablation + layout condition), timestep [b]."""
+    from oracle import controlnet as ocn, mvgen as om, unet as ou
+    from panfusion_b200.mvgen import MultiViewBaseModel
+    cfg = ou.TINY_CONFIG
+    pano_unet = ou.build_unet(cfg, seed=2)
+    cn = ocn.build_controlnet(ou.build_unet(cfg, seed=3), seed=4)
+    orc = om.MultiViewBaseModel(None, pano_unet, pano_cn=cn).eval()
+    mine = MultiViewBaseModel(None, pano_unet, pano_cn=cn, compute_dtype=torch.float16)
+    g = torch.Generator().manual_seed(0)
+    pano = torch.randn(2, 1, 4, 16, 32, generator=g)
+    text = torch.randn(2, 1, 77, cfg["cross_attention_dim"], generator=g)
+    cond = torch.rand(2, 1, 3, 128, 256, generator=g)
+    t = torch.tensor([981, 501])
+    with torch.no_grad():
+        _, ref = orc(None, pano, t, None, text, None, None, cond)
+    s, got = mine(None, pano.to(cuda_device), t.to(cuda_device), None, text.to(cuda_device), None, None,
+                  cond.to(cuda_device))
+    assert s is None
+    _check("pano-only + ControlNet", got, ref, torch.float16)
+
+
+def test_mvgen_icosahedron_20_views(cuda_device):
+    """BASELINE config 4's camera rig (utils/pano.py:34-71: 20 icosahedron face centres, phi != 0) at CPU-checkable
+    size: 20 views 16x16 + pano 16x32, CFG-style batch of 2, against the oracle."""
+    import sys
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from bench import icosahedron_cameras
+    from oracle import mvgen as om, sampler as osamp, synth, unet as ou
+    from panfusion_b200.mvgen import MultiViewBaseModel
+    cfg, dtype, m = ou.TINY_CONFIG, torch.float16, 20
+    orc = synth.build_model(om.MultiViewBaseModel, cfg, seed=0)
+    mine = MultiViewBaseModel(orc.unet, orc.pano_unet, compute_dtype=dtype)
+    mine.load_state_dict(orc.state_dict())
+    theta, phi = icosahedron_cameras()
+    assert len(theta) == 20 and abs(abs(phi[0]) - 52.6226) < 1e-3 and abs(abs(phi[5]) - 10.8123) < 1e-3
+    cams = dict(FoV=torch.full((2, m), 90.0), theta=torch.tensor(theta, dtype=torch.float32).repeat(2, 1),
+                phi=torch.tensor(phi, dtype=torch.float32).repeat(2, 1))
+    g = torch.Generator().manual_seed(0)
+    pano = torch.randn(2, 1, 4, 16, 32, generator=g)
+    lat = osamp.init_noise(pano, 16, 16, cams)
+    ts = torch.full((2, m), 501, dtype=torch.long)
+    prompt = torch.randn(2, 1, 77, cfg["cross_attention_dim"], generator=g).repeat(1, m, 1, 1)
+    inp = dict(latents=lat, pano_latent=pano, timestep=ts, prompt_embd=prompt, pano_prompt_embd=prompt[:, :1].clone(),
+               cameras=cams)
+    with torch.no_grad():
+        rs, rp = orc(**inp)
+    s, p = mine(**_to_dev(inp, cuda_device))
+    _check("icosahedron-20 sample", s, rs, dtype)
+    _check("icosahedron-20 pano", p, rp, dtype)
+
+
+def test_identity_keyed_caches_survive_address_reuse(cuda_device):
+    """The text K/V (and layout-condition) caches are keyed on tensor identity; a NEW prompt tensor that lands on the
+    address of a freed one must not hit the stale entry."""
+    from oracle import synth, unet as ou
+    cfg, dtype = ou.TINY_CONFIG, torch.float16
+    orc, mine = _build_cn_pair(cuda_device, cfg, dtype, False)
+    inp = synth.step_inputs(2, (16, 32), (16, 16), cfg["cross_attention_dim"], seed=0)
+    inp.update(synth.layout_conds(1, 2, (16, 32), (16, 16), seed=5))
+    cu = _to_dev(inp, cuda_device)
+    mine(**cu)
+    g = torch.Generator().manual_seed(77)
+    new_prompt = torch.randn(inp["pano_prompt_embd"].shape, generator=g)
+    new_cond = torch.rand(inp["pano_layout_cond"].shape, generator=g)
+    for _ in range(3):  # free + reallocate same-shaped tensors: the allocator hands the same blocks back
+        del cu["pano_prompt_embd"], cu["pano_layout_cond"]
+        cu["pano_prompt_embd"], cu["pano_layout_cond"] = new_prompt.to(cuda_device), new_cond.to(cuda_device)
+        s, p = mine(**cu)
+    mine.prepare(cuda_device, dtype)  # drops every cache
+    s_ref, p_ref = mine(**cu)
+    assert torch.equal(p, p_ref) and torch.equal(s, s_ref)

@@ -63,3 +63,43 @@ def test_three_steps_vs_oracle_and_graph_replay(cuda_device, dtype):
     _, gp_back = s.denoise(dev(lat), dev(pano), dev(prompt), dev(pano_prompt), cams, num_steps=n)
     ref_back = torch.roll(rp, int(-n * 90 / 360 * 32), dims=-1)
     assert (gp_back.cpu() - ref_back).abs().max().item() / ref_back.abs().max().item() < 3e-2
+
+
+def test_layout_conditioned_steps_vs_oracle_and_graph_replay(cuda_device):
+    """BASELINE config 5 through the sampling loop: the panorama layout condition is rolled a quarter turn per step
+    (PanFusion.py:152-153); 5 steps so that phase 0's graph and cached conditioning features are reused."""
+    from oracle import mvgen as om, sampler as osamp, synth, unet as ou
+    from panfusion_b200.mvgen import MultiViewBaseModel
+    from panfusion_b200.sampler import PanFusionSampler
+    cfg, dtype = ou.TINY_CONFIG, torch.float16
+    orc = synth.build_model_cn(om.MultiViewBaseModel, cfg, seed=0)
+    mine = MultiViewBaseModel(orc.unet, orc.pano_unet, pano_cn=orc.pano_cn, compute_dtype=dtype)
+    mine.load_state_dict(orc.state_dict())
+    mine.prepare(cuda_device, dtype)
+    m = 4
+    cams = osamp.horizon_cameras(m)
+    g = torch.Generator().manual_seed(0)
+    pano = torch.randn(1, 1, 4, 16, 32, generator=g)
+    lat = osamp.init_noise(pano, 16, 16, cams)
+    text = torch.randn(1, 1, 77, cfg["cross_attention_dim"], generator=g)
+    null = torch.randn(1, 1, 77, cfg["cross_attention_dim"], generator=g)
+    pano_prompt = torch.cat([null, text])
+    prompt = torch.cat([null.repeat(1, m, 1, 1), text.repeat(1, m, 1, 1)])
+    cond = synth.layout_conds(1, m, (16, 32), (16, 16), seed=5)["pano_layout_cond"]
+    n = 5
+    with torch.no_grad():
+        rl, rp, _ = osamp.denoise_steps(orc, lat, pano, prompt, pano_prompt, cams, n, pano_layout_cond=cond)
+        rl0, rp0, _ = osamp.denoise_steps(orc, lat, pano, prompt, pano_prompt, cams, n)
+    assert (rp - rp0).abs().max().item() > 0.02 * rp0.abs().max().item()  # the condition matters
+    dev = lambda t: t.to(cuda_device)
+    outs = {}
+    for graph in (False, True):
+        s = PanFusionSampler(mine, use_cuda_graph=graph)
+        gl, gp = s.denoise(dev(lat), dev(pano), dev(prompt), dev(pano_prompt), cams, num_steps=n, rotate_back=False,
+                           pano_layout_cond=dev(cond))
+        outs[graph] = (gl.cpu(), gp.cpu())
+    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
+    for name, got, ref in (("latents", outs[True][0], rl), ("pano", outs[True][1], rp)):
+        err = (got - ref).abs().max().item() / ref.abs().max().item()
+        print(f"[parity] {n}-step layout-conditioned sampler {name}: max err {err:.3e} of max|ref|")
+        assert err < 3e-2

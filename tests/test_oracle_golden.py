@@ -81,6 +81,24 @@ def test_mvgen_tiny_matches_reference_golden():
     np.testing.assert_allclose(p.numpy(), gold["pano_sample"], rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("tag,pers", [("tiny_cn", False), ("tiny_cn2", True)])
+def test_mvgen_controlnet_matches_reference_golden(tag, pers):
+    """Layout-conditioned step (BASELINE config 5): golden = reference MVGenModel.py run around the ControlNet
+    restatement; the condition must change the output (zero convs are redrawn)."""
+    gold = np.load(GOLD / f"mvgen_{tag}.npz")
+    model = synth.build_model_cn(om.MultiViewBaseModel, ou.TINY_CONFIG, seed=0, pers=pers)
+    inp = synth.step_inputs(2, (16, 32), (16, 16), ou.TINY_CONFIG["cross_attention_dim"], seed=0)
+    inp.update(synth.layout_conds(1, 2, (16, 32), (16, 16), seed=5, pers=pers))
+    with torch.no_grad():
+        s, p = model(**inp)
+        s0, p0 = model(**{**inp, "pano_layout_cond": None, "pers_layout_cond": None})
+    np.testing.assert_allclose(s.numpy(), gold["sample"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(p.numpy(), gold["pano_sample"], rtol=1e-4, atol=1e-4)
+    assert (p - p0).abs().max() > 0.05
+    base = np.load(GOLD / "mvgen_tiny.npz")
+    np.testing.assert_allclose(p0.numpy(), base["pano_sample"], rtol=1e-4, atol=1e-4)  # cond=None == no ControlNet
+
+
 def test_pano_only_branch():
     """unet=None (PanoOnly ablation, models/pano/PanoOnly.py:13): timestep is [b], no EPPA blocks."""
     pano_unet = ou.build_unet(ou.TINY_CONFIG, seed=2)
