@@ -194,6 +194,11 @@ int pf_conv_out(const void* xp, int dtype, const float* w, const float* bias, fl
 /* strided 2-D copy of 16-bit rows (skip concatenation, torch.cat at MVGenModel.py:223,231,246,254) */
 int pf_copy2d(const void* src, int src_ld, void* dst, int dst_ld, long long rows, int cols, void* stream);
 
+/* pad_pano (utils/pano.py:74-99): out[r, j] = x[r, (j - pad) mod W] for j in [0, W + 2*pad) — circular padding of the
+ * longitude axis of a contiguous tensor whose leading dims are flattened into `rows`; any pad >= 1 (F.pad's circular
+ * mode limits pad <= W, this does not). elem_bytes in {1, 2, 4, 8}. */
+int pf_pad_pano(const void* x, void* out, int elem_bytes, long long rows, int W, int pad, void* stream);
+
 /* diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0) (MVGenModel.py:55,59): t fp32 [n] -> [n, dim] */
 int pf_timestep_embed(const float* t, void* out, int dtype, int n, int dim, void* stream);
 

@@ -181,6 +181,20 @@ copy2d_kernel(const uint16_t* __restrict__ src, int src_ld, uint16_t* __restrict
   *reinterpret_cast<uint4*>(dst + r * dst_ld + v * 8) = __ldg(reinterpret_cast<const uint4*>(src + r * src_ld + v * 8));
 }
 
+// pad_pano (utils/pano.py:74-99): circular padding of the last (longitude) axis; rows = every leading dim flattened
+template <typename T>
+__global__ void __launch_bounds__(256)
+pad_pano_kernel(const T* __restrict__ x, T* __restrict__ out, long long rows, int W, int pad) {
+  const int Wo = W + 2 * pad;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Wo) return;
+  const long long r = idx / Wo;
+  int j = int(idx % Wo) - pad;
+  j %= W;
+  if (j < 0) j += W;
+  out[idx] = __ldg(x + r * W + j);
+}
+
 // diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos(t f_i) | sin(t f_i)], f_i = 10000^(-i/half)
 template <bool BF16>
 __global__ void timestep_embed_kernel(const float* __restrict__ t, uint16_t* __restrict__ out, int n, int dim) {
@@ -288,6 +302,26 @@ extern "C" int pf_copy2d(const void* src, int src_ld, void* dst, int dst_ld, lon
   copy2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint16_t*>(src), src_ld, static_cast<uint16_t*>(dst), dst_ld, rows, cols);
   PF_CHECK_LAUNCH("copy2d_kernel");
+  return PF_OK;
+}
+
+extern "C" int pf_pad_pano(const void* x, void* out, int elem_bytes, long long rows, int W, int pad, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(x && out, "pf_pad_pano: null pointer");
+  PF_CHECK_ARG(elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4 || elem_bytes == 8,
+               "pf_pad_pano: elem_bytes must be 1, 2, 4 or 8");
+  PF_CHECK_ARG(rows > 0 && W > 0 && pad > 0, "pf_pad_pano: bad shape rows=%lld W=%d pad=%d", rows, W, pad);
+  const long long total = rows * (W + 2LL * pad);
+  PF_CHECK_ARG(total <= 2147483647LL * 256, "pf_pad_pano: tensor too large");
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (elem_bytes) {
+    case 1: pad_pano_kernel<uint8_t><<<blocks, 256, 0, st>>>(static_cast<const uint8_t*>(x), static_cast<uint8_t*>(out), rows, W, pad); break;
+    case 2: pad_pano_kernel<uint16_t><<<blocks, 256, 0, st>>>(static_cast<const uint16_t*>(x), static_cast<uint16_t*>(out), rows, W, pad); break;
+    case 4: pad_pano_kernel<uint32_t><<<blocks, 256, 0, st>>>(static_cast<const uint32_t*>(x), static_cast<uint32_t*>(out), rows, W, pad); break;
+    default: pad_pano_kernel<uint64_t><<<blocks, 256, 0, st>>>(static_cast<const uint64_t*>(x), static_cast<uint64_t*>(out), rows, W, pad); break;
+  }
+  PF_CHECK_LAUNCH("pad_pano_kernel");
   return PF_OK;
 }
 

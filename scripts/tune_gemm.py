@@ -1,5 +1,7 @@
 """Measure, on the B200, the best tap-GEMM tile width (block_n) for every GEMM shape of a C2 denoise step and write
-panfusion_b200/gemm_tuning.json (copied back from gpurun_out/). Usage: python scripts/tune_gemm.py [out.json]"""
+panfusion_b200/gemm_tuning.json (copied back from gpurun_out/).
+Usage: python scripts/tune_gemm.py [out.json] [workload:layout,...]   e.g.  c2:1x1,c2:2x1,c2:2x2,c2:2x4,c5:1x1
+(layouts other than 1x1 are the rank-local shapes of the sharded step, collected with scripts/rank_emulate.py)"""
 import collections
 import json
 import sys
@@ -9,34 +11,40 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import torch  # noqa: E402
 
-import bench  # noqa: E402
-from panfusion_b200 import geometry, ops, sd2_unet  # noqa: E402
-from panfusion_b200.mvgen import MultiViewBaseModel  # noqa: E402
-from panfusion_b200.sampler import PanFusionSampler  # noqa: E402
+sys.path.insert(0, str(ROOT / "scripts"))
+from panfusion_b200 import ops  # noqa: E402
 
 
-def main():
-    out_path = Path(sys.argv[1] if len(sys.argv) > 1 else ROOT / "gpurun_out" / "gemm_tuning.json")
-    dev = torch.device("cuda:0")
-    dt = torch.bfloat16
-    model = MultiViewBaseModel(sd2_unet.build_synthetic(seed=1, device=dev), sd2_unet.build_synthetic(seed=2, device=dev),
-                               compute_dtype=dt, overlap_branches=False).to(dev).eval()
-    model.prepare(dev, dt)
-    sampler = PanFusionSampler(model, use_cuda_graph=False)
-    wl = bench.WORKLOADS["c2"]
-    inp = bench.synthetic_inputs(wl, 1024, dev, sampler)
-    pano = inp["pano"].to(dev)
-    cf = {k: v.flatten(0, 1) for k, v in inp["cams"].items()}
-    lat = geometry.e2p(pano.expand(-1, wl["m"], -1, -1, -1).flatten(0, 1).contiguous(), cf["FoV"], cf["theta"], cf["phi"],
-                       wl["pers_hw"], mode="nearest")[None]
-    sampler.start(lat, pano, inp["prompt"].to(dev), inp["pano_prompt"].to(dev), inp["cams"])
+def collect(workload, layout, dev, dt):
+    """GEMM shapes of one (rank-local) denoise step of `workload` under `layout` = (batch_shards, view_shards)."""
+    from rank_emulate import build
+    model, sampler = build(workload, dev, dt, layout, graph=False, overlap=False)
     sampler.step(0)
     ops.GEMM_LOG = []
     sampler.step(1)
     torch.cuda.synchronize()
     shapes = collections.Counter(ops.GEMM_LOG)
     ops.GEMM_LOG = None
-    print(f"{len(shapes)} distinct GEMM shapes, {sum(shapes.values())} launches")
+    del model, sampler
+    torch.cuda.empty_cache()
+    return shapes
+
+
+def main():
+    out_path = Path(sys.argv[1] if len(sys.argv) > 1 else ROOT / "gpurun_out" / "gemm_tuning.json")
+    # workload:layout list; the single-GPU C2 step first (its counts weight the printed totals)
+    spec = sys.argv[2] if len(sys.argv) > 2 else "c2:1x1"
+    dev = torch.device("cuda:0")
+    dt = torch.bfloat16
+    shapes = collections.Counter()
+    for item in spec.split(","):
+        wl, lay = item.split(":")
+        got = collect(wl, tuple(int(v) for v in lay.split("x")), dev, dt)
+        new = [k for k in got if k not in shapes]
+        print(f"{item}: {len(got)} distinct GEMM shapes ({len(new)} new), {sum(got.values())} launches", flush=True)
+        for k in new:
+            shapes[k] = got[k]
+    print(f"{len(shapes)} distinct GEMM shapes in total")
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     results, table = [], {}

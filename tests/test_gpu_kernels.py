@@ -179,3 +179,23 @@ def test_eppa_tables_vs_oracle(cuda_device, ph, pw, eh, ew, V, m):
         # argument; allow a few ulp
         torch.testing.assert_close(gp.cpu(), rp, rtol=0, atol=5e-6)
         torch.testing.assert_close(ge.cpu(), re, rtol=0, atol=5e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.uint8])
+def test_pad_pano_bit_exact(cuda_device, dtype):
+    """pad_pano / unpad_pano (utils/pano.py:74-105): 4-D and 5-D, every dtype width, against the oracle restatement
+    (itself pinned to the reference in tests/test_oracle_golden.py)."""
+    from oracle.eppa import pad_pano as ref_pad
+    from panfusion_b200.pano import pad_pano, unpad_pano
+    g = torch.Generator().manual_seed(3)
+    for shape in ((2, 3, 5, 16), (2, 2, 3, 4, 12)):
+        x = (torch.rand(shape, generator=g) * 200).to(dtype)
+        for p in (1, 2, 8):
+            got = pad_pano(x.to(cuda_device), p)
+            ref = ref_pad(x.float(), p).to(dtype)
+            assert got.shape == ref.shape and torch.equal(got.cpu(), ref)
+            assert torch.equal(unpad_pano(got, p).cpu(), x)
+    xd = x.to(cuda_device)
+    assert pad_pano(xd, 0) is xd and unpad_pano(xd, 0) is xd
+    with pytest.raises(NotImplementedError):
+        pad_pano(torch.zeros(3, 4, 5, device=cuda_device), 1)
