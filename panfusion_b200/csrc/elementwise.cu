@@ -173,6 +173,8 @@ conv_out_kernel(const uint16_t* __restrict__ xp, const float* __restrict__ w, co
 __global__ void __launch_bounds__(256)
 copy2d_kernel(const uint16_t* __restrict__ src, int src_ld, uint16_t* __restrict__ dst, int dst_ld, long long rows,
               int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vecs = cols / 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * vecs) return;
@@ -299,8 +301,8 @@ extern "C" int pf_copy2d(const void* src, int src_ld, void* dst, int dst_ld, lon
                "pf_copy2d: bad shape rows=%lld cols=%d", rows, cols);
   PF_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "pf_copy2d: pointers must be 16-byte aligned");
   const long long total = rows * (cols / 8);
-  copy2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint16_t*>(src), src_ld, static_cast<uint16_t*>(dst), dst_ld, rows, cols);
+  launch_pdl(copy2d_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+             static_cast<const uint16_t*>(src), src_ld, static_cast<uint16_t*>(dst), dst_ld, rows, cols);
   PF_CHECK_LAUNCH("copy2d_kernel");
   return PF_OK;
 }

@@ -121,6 +121,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* o_done = p_full + 1;   // P V of the tile has completed
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 1);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x % p.H;  // heads fastest: CTAs sharing a bias tile run together (L2 reuse)
   const int qt = blockIdx.x / p.H;
@@ -151,6 +152,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // Q/K/V (and the bias flags) written by the predecessor are visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -390,7 +392,7 @@ static int launch_fmha(const pf_fmha_args* a, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(((a->Lq + FA_BLOCK_M - 1) / FA_BLOCK_M) * a->H, a->B);
-  kern<<<grid, FA_THREADS, SMEM, st>>>(tmQ, tmK, tmV, p);
+  if ((rc = check_cuda(launch_pdl(kern, grid, dim3(FA_THREADS), SMEM, st, tmQ, tmK, tmV, p), "launch(fmha)"))) return rc;
   PF_CHECK_LAUNCH("fmha_fwd_kernel");
   return PF_OK;
 }

@@ -50,6 +50,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(stg_empty + 2);
   float* s_bias = reinterpret_cast<float*>(staging + 2 * STAGING_BYTES + 256);  // [2][BLOCK_N]
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.N / BLOCK_N;
   const int m_tiles = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
@@ -79,6 +80,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // on-chip prologue done; the predecessor's results are visible from here on
 
   if (warp == 0) {
     // ---------------------------------- TMA producer ----------------------------------
@@ -451,7 +453,7 @@ static int launch_persist(const pf_gemm_args* a, const GemmKernelParams& kp, cud
         return rc;
       attr_set = true;
     }
-    kern<<<grid, PG_THREADS, SMEM, st>>>(tmA, tmB, tmC, tmR, kp);
+    if ((rc = check_cuda(launch_pdl(kern, dim3(grid), dim3(PG_THREADS), SMEM, st, tmA, tmB, tmC, tmR, kp), "launch(gemm_persist)"))) return rc;
   } else {
     auto kern = gemm_persist_kernel<BLOCK_N, STAGES, false, EPI_TMA>;
     static bool attr_set = false;
@@ -461,7 +463,7 @@ static int launch_persist(const pf_gemm_args* a, const GemmKernelParams& kp, cud
         return rc;
       attr_set = true;
     }
-    kern<<<grid, PG_THREADS, SMEM, st>>>(tmA, tmB, tmC, tmR, kp);
+    if ((rc = check_cuda(launch_pdl(kern, dim3(grid), dim3(PG_THREADS), SMEM, st, tmA, tmB, tmC, tmR, kp), "launch(gemm_persist)"))) return rc;
   }
   PF_CHECK_LAUNCH("gemm_persist_kernel");
   return PF_OK;

@@ -56,6 +56,7 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_full_bar + 1);
   float* s_bias = reinterpret_cast<float*>(staging + STAGING_BYTES + 128);  // [BLOCK_N]
 
+  pdl_launch_dependents();  // the next kernel of the stream may start its prologue while this one runs
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = p.N / BLOCK_N;
@@ -96,6 +97,7 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // everything above touched only on-chip state; operands of the predecessor are visible from here on
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -542,7 +544,7 @@ static int launch_gemm(const pf_gemm_args* a, const GemmKernelParams& kp, cudaSt
       if (rc) return rc;
       attr_set = true;
     }
-    kern<<<grid, GEMM_THREADS, SMEM, st>>>(tmA, tmB, tmC, tmR, kp);
+    if (int rc = check_cuda(launch_pdl(kern, grid, dim3(GEMM_THREADS), SMEM, st, tmA, tmB, tmC, tmR, kp), "launch(gemm)")) return rc;
   } else {
     auto kern = gemm_taps_kernel<BLOCK_N, STAGES, false, EPI_TMA, false>;
     static bool attr_set = false;
@@ -552,7 +554,7 @@ static int launch_gemm(const pf_gemm_args* a, const GemmKernelParams& kp, cudaSt
       if (rc) return rc;
       attr_set = true;
     }
-    kern<<<grid, GEMM_THREADS, SMEM, st>>>(tmA, tmB, tmC, tmR, kp);
+    if (int rc = check_cuda(launch_pdl(kern, grid, dim3(GEMM_THREADS), SMEM, st, tmA, tmB, tmC, tmR, kp), "launch(gemm)")) return rc;
   }
   PF_CHECK_LAUNCH("gemm_taps_kernel");
   return PF_OK;
@@ -581,13 +583,15 @@ static int launch_gemm_pair(const pf_gemm_args* a, const GemmKernelParams& kp, c
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   if (a->dtype == PF_BF16) {
     auto kern = gemm_taps_kernel<BLOCK_N, STAGES, true, false, true>;
     static bool attr_set = false;

@@ -27,6 +27,8 @@ gn_partial_kernel(const uint16_t* __restrict__ x, int H, int W, int C, int ld, i
                   float* __restrict__ ws, int* __restrict__ counters, float count, float eps,
                   float* __restrict__ mean_rstd) {
   extern __shared__ float s_acc[];  // [ppi][2][C] per-pixel-lane partials (fixed-order reduction: deterministic)
+  pdl_launch_dependents();
+  pdl_wait();
   const int vecs = C / 8;
   const int ppi = blockDim.x / vecs;
   const int v = threadIdx.x % vecs, pl = threadIdx.x / vecs;
@@ -136,6 +138,8 @@ struct PrepParams {
 // row's image is built once per CTA in shared memory and the inner loop is load -> 8 FMA (+SiLU) -> store.
 template <bool BF16>
 __global__ void __launch_bounds__(256) conv_prep_kernel(const PrepParams p) {
+  pdl_launch_dependents();
+  pdl_wait();  // the GroupNorm statistics staged below come from the predecessor
   extern __shared__ float s_ss[];  // [2][C] scale, shift
   const int vecs = p.C / 8;
   int rowid = blockIdx.y;
@@ -216,11 +220,13 @@ layernorm_kernel(const uint16_t* __restrict__ x, int ldx, const float* __restric
   const int vecs = C / 8;
   // affine parameters staged once per CTA in shared memory (each warp then visits many tokens)
   extern __shared__ float s_gb[];  // [2][C]
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  pdl_launch_dependents();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {  // weights: constant during a step, safe before pdl_wait
     s_gb[c] = __ldg(gamma + c);
     s_gb[C + c] = __ldg(beta + c);
   }
   __syncthreads();
+  pdl_wait();
   for (int tok = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tok < T; tok += warps_total) {
     float f[MAXV][8];
     float sum = 0.f;
@@ -306,11 +312,11 @@ extern "C" int pf_groupnorm_stats(const void* x, int dtype, int N, int H, int W,
   const size_t smem = 2 * (size_t)C * ppi * sizeof(float);
   const float count = float(H) * float(W + 2 * circ) * float(C / groups);
   if (dtype == PF_BF16)
-    gn_partial_kernel<true><<<grid, threads, smem, st>>>(static_cast<const uint16_t*>(x), H, W, C, ld, groups, circ, ws,
-                                                         counters, count, eps, mean_rstd);
+    launch_pdl(gn_partial_kernel<true>, grid, dim3(threads), smem, st, static_cast<const uint16_t*>(x), H, W, C, ld, groups,
+               circ, ws, counters, count, eps, mean_rstd);
   else
-    gn_partial_kernel<false><<<grid, threads, smem, st>>>(static_cast<const uint16_t*>(x), H, W, C, ld, groups, circ, ws,
-                                                          counters, count, eps, mean_rstd);
+    launch_pdl(gn_partial_kernel<false>, grid, dim3(threads), smem, st, static_cast<const uint16_t*>(x), H, W, C, ld, groups,
+               circ, ws, counters, count, eps, mean_rstd);
   PF_CHECK_LAUNCH("gn_partial_kernel");
   return PF_OK;
 }
@@ -355,8 +361,8 @@ extern "C" int pf_conv_prep(const void* x, void* out, int dtype, int N, int H, i
     set_error("pf_conv_prep: N*phases*Ho = %lld exceeds 65535", rows);
     return PF_ERR_UNSUPPORTED;
   }
-  if (dtype == PF_BF16) conv_prep_kernel<true><<<grid, 256, smem, st>>>(p);
-  else conv_prep_kernel<false><<<grid, 256, smem, st>>>(p);
+  if (dtype == PF_BF16) launch_pdl(conv_prep_kernel<true>, grid, dim3(256), smem, st, p);
+  else launch_pdl(conv_prep_kernel<false>, grid, dim3(256), smem, st, p);
   PF_CHECK_LAUNCH("conv_prep_kernel");
   return PF_OK;
 }
@@ -375,7 +381,7 @@ extern "C" int pf_layernorm(const void* x, int ldx, void* out, int ldo, int dtyp
   const uint16_t* xi = static_cast<const uint16_t*>(x);
   uint16_t* xo = static_cast<uint16_t*>(out);
   const int rounds = (C / 8 + 31) / 32;
-#define PF_LN(BF, MV) layernorm_kernel<BF, MV><<<blocks, 256, 2 * (size_t)C * sizeof(float), st>>>(xi, ldx, pe, pe_rows, T, C, gamma, beta, eps, xo, ldo)
+#define PF_LN(BF, MV) launch_pdl(layernorm_kernel<BF, MV>, dim3(blocks), dim3(256), 2 * (size_t)C * sizeof(float), st, xi, ldx, pe, pe_rows, T, C, gamma, beta, eps, xo, ldo)
   if (dtype == PF_BF16) {
     if (rounds <= 2) PF_LN(true, 2); else if (rounds <= 5) PF_LN(true, 5); else PF_LN(true, 8);
   } else {

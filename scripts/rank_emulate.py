@@ -87,11 +87,45 @@ def main():
     ap.add_argument("--layouts", default="1x1,2x1,2x2,2x4")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--whole-graph", action="store_true", help="keep the stand-in collectives INSIDE one graph")
+    ap.add_argument("--no-overlap", action="store_true", help="panorama branch on the main stream (serialised)")
+    ap.add_argument("--pano-only", action="store_true", help="time the panorama branch alone (unet=None), batch = "
+                    "2 / batch_shards, as a CUDA graph of MultiViewBaseModel.forward")
     args = ap.parse_args()
     dev, dt = torch.device("cuda:0"), torch.bfloat16
     for lay in args.layouts.split(","):
         layout = tuple(int(v) for v in lay.split("x"))
-        model, sampler = build(args.workload, dev, dt, layout, args.whole_graph)
+        if args.pano_only:
+            wl = bench.WORKLOADS[args.workload]
+            b = 2 // layout[0]
+            model = MultiViewBaseModel(None, sd2_unet.build_synthetic(seed=2, device=dev), compute_dtype=dt).to(dev).eval()
+            model.prepare(dev, dt)
+            g = torch.Generator(device=dev).manual_seed(0)
+            pano = torch.randn(b, 1, 4, *wl["pano_hw"], device=dev, generator=g)
+            text = torch.randn(b, 1, 77, 1024, device=dev, generator=g)
+            t = torch.full((b,), 501, device=dev)
+            fwd = lambda: model(None, pano, t, None, text, None)
+            fwd()
+            torch.cuda.synchronize()
+            l0 = ops.LAUNCHES
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fwd()
+            n_launch = ops.LAUNCHES - l0
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            print(json.dumps(dict(workload=args.workload, pano_only_batch=b,
+                                  ms=round(e0.elapsed_time(e1) / args.steps, 3), launches=n_launch)), flush=True)
+            del model, graph
+            torch.cuda.empty_cache()
+            continue
+        model, sampler = build(args.workload, dev, dt, layout, args.whole_graph, overlap=not args.no_overlap)
         for i in range(4 + 3):
             sampler.step(i)
         torch.cuda.synchronize()
@@ -103,7 +137,8 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
         print(json.dumps(dict(workload=args.workload, layout=lay, whole_graph=args.whole_graph,
-                              ms_per_rank_step=round(ms, 3), launches=sampler.launches_per_step)), flush=True)
+                              overlap=not args.no_overlap, ms_per_rank_step=round(ms, 3),
+                              launches=sampler.launches_per_step)), flush=True)
         del model, sampler
         torch.cuda.empty_cache()
 
