@@ -199,6 +199,17 @@ int pf_copy2d(const void* src, int src_ld, void* dst, int dst_ld, long long rows
  * mode limits pad <= W, this does not). elem_bytes in {1, 2, 4, 8}. */
 int pf_pad_pano(const void* x, void* out, int elem_bytes, long long rows, int W, int pad, void* stream);
 
+/* out[r, :cols] = softmax(scale * s[r, :cols]) — fp32 logits [rows, ld] -> 16-bit probabilities [rows, ldo].
+ * The VAE mid-block attention (diffusers AutoencoderKL [3P], called through decode_latent, PanoGenerator.py:272-278)
+ * has ONE head of width 512, outside the flash kernel's head sizes: it runs as pf_gemm_taps (Q K^T, fp32 out) ->
+ * pf_softmax_rows -> pf_gemm_taps (P V). */
+int pf_softmax_rows(const float* s, long long ld, void* out, long long ldo, int dtype, long long rows, int cols,
+                    float scale, void* stream);
+
+/* tensor_to_image (models/modules/utils.py:9-15): x fp32 [n, C, H, W] in [-1, 1] -> uint8 [n, H, W, C] =
+ * round(clamp(x / 2 + 0.5, 0, 1) * 255), round-half-to-even like torch.round. */
+int pf_tensor_to_image(const float* x, unsigned char* out, long long n, int C, int H, int W, void* stream);
+
 /* diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0) (MVGenModel.py:55,59): t fp32 [n] -> [n, dim] */
 int pf_timestep_embed(const float* t, void* out, int dtype, int n, int dim, void* stream);
 

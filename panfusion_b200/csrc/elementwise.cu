@@ -197,6 +197,59 @@ pad_pano_kernel(const T* __restrict__ x, T* __restrict__ out, long long rows, in
   out[idx] = __ldg(x + r * W + j);
 }
 
+// row softmax of fp32 logits -> 16-bit probabilities (the VAE mid-block attention: one head of width 512, computed as
+// two tap-GEMMs around this kernel). One CTA per row; three passes over a row that stays in L1/L2.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ s, long long ld, uint16_t* __restrict__ out, long long ldo, int cols,
+                    float scale) {
+  __shared__ float red[8];
+  const float* row = s + (size_t)blockIdx.x * ld;
+  uint16_t* orow = out + (size_t)blockIdx.x * ldo;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, row[c]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) sum += expf((row[c] - m) * scale);
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += red[w];
+  const float inv = 1.0f / sum;
+  for (int c = 2 * threadIdx.x; c < cols; c += 512) {
+    const float a = expf((row[c] - m) * scale) * inv;
+    const float b = c + 1 < cols ? expf((row[c + 1] - m) * scale) * inv : 0.f;
+    if (c + 1 < cols) *reinterpret_cast<uint32_t*>(orow + c) = pack2<BF16>(a, b);
+    else orow[c] = (uint16_t)(pack2<BF16>(a, 0.f) & 0xffffu);
+  }
+}
+
+// tensor_to_image (models/modules/utils.py:9-15): float [-1,1] planes [n, C, H, W] -> uint8 [n, H, W, C]
+__global__ void __launch_bounds__(256)
+tensor_to_image_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, long long total, int C, int H, int W) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over the OUTPUT [n, H, W, C]
+  if (idx >= total) return;
+  const int c = int(idx % C);
+  long long r = idx / C;
+  const int xx = int(r % W);
+  r /= W;
+  const int yy = int(r % H);
+  const long long n = r / H;
+  float v = __ldg(x + ((n * C + c) * H + yy) * (long long)W + xx) / 2.0f + 0.5f;
+  v = fminf(fmaxf(v, 0.f), 1.f);
+  out[idx] = (uint8_t)rintf(v * 255.0f);
+}
+
 // diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos(t f_i) | sin(t f_i)], f_i = 10000^(-i/half)
 template <bool BF16>
 __global__ void timestep_embed_kernel(const float* __restrict__ t, uint16_t* __restrict__ out, int n, int dim) {
@@ -324,6 +377,31 @@ extern "C" int pf_pad_pano(const void* x, void* out, int elem_bytes, long long r
     default: pad_pano_kernel<uint64_t><<<blocks, 256, 0, st>>>(static_cast<const uint64_t*>(x), static_cast<uint64_t*>(out), rows, W, pad); break;
   }
   PF_CHECK_LAUNCH("pad_pano_kernel");
+  return PF_OK;
+}
+
+extern "C" int pf_softmax_rows(const float* s, long long ld, void* out, long long ldo, int dtype, long long rows,
+                               int cols, float scale, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(s && out, "pf_softmax_rows: null pointer");
+  PF_CHECK_ARG(dtype == PF_BF16 || dtype == PF_F16, "pf_softmax_rows: 16-bit output dtype required");
+  PF_CHECK_ARG(rows > 0 && rows <= 2147483647LL && cols > 0 && ld >= cols && ldo >= cols && ldo % 2 == 0,
+               "pf_softmax_rows: bad shape rows=%lld cols=%d", rows, cols);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == PF_BF16) softmax_rows_kernel<true><<<(unsigned)rows, 256, 0, st>>>(s, ld, static_cast<uint16_t*>(out), ldo, cols, scale);
+  else softmax_rows_kernel<false><<<(unsigned)rows, 256, 0, st>>>(s, ld, static_cast<uint16_t*>(out), ldo, cols, scale);
+  PF_CHECK_LAUNCH("softmax_rows_kernel");
+  return PF_OK;
+}
+
+extern "C" int pf_tensor_to_image(const float* x, unsigned char* out, long long n, int C, int H, int W, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(x && out, "pf_tensor_to_image: null pointer");
+  PF_CHECK_ARG(n > 0 && C > 0 && H > 0 && W > 0, "pf_tensor_to_image: bad shape");
+  const long long total = n * C * H * W;
+  PF_CHECK_ARG(total <= 2147483647LL * 256, "pf_tensor_to_image: tensor too large");
+  tensor_to_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, total, C, H, W);
+  PF_CHECK_LAUNCH("tensor_to_image_kernel");
   return PF_OK;
 }
 

@@ -253,6 +253,28 @@ def copy2d(src: Tensor, dst: Tensor) -> None:
     _lib.check(_lib.lib().pf_copy2d(_vp(src), src.stride(0), _vp(dst), dst.stride(0), C.c_longlong(rows), cols, _st()))
 
 
+def softmax_rows(s: Tensor, out: Tensor, scale: float) -> Tensor:
+    """out[r] = softmax(scale * s[r]) — s fp32 [rows, cols], out 16-bit [rows, cols] (row strides free)."""
+    assert s.dtype == torch.float32 and s.dim() == 2 and out.shape == s.shape and s.stride(1) == 1 and out.stride(1) == 1
+    _count(1)
+    _lib.check(_lib.lib().pf_softmax_rows(_vp(s), C.c_longlong(s.stride(0)), _vp(out), C.c_longlong(out.stride(0)),
+                                          _lib.dtype_code(out.dtype), C.c_longlong(s.shape[0]), s.shape[1], _f(scale),
+                                          _st()))
+    return out
+
+
+def tensor_to_image(x: Tensor) -> Tensor:
+    """x fp32 [..., C, H, W] in [-1, 1] -> uint8 [..., H, W, C] on the device."""
+    assert x.dtype == torch.float32 and x.dim() >= 3
+    x = x.contiguous()
+    Cc, H, W = x.shape[-3:]
+    n = x.numel() // (Cc * H * W)
+    out = torch.empty((*x.shape[:-3], H, W, Cc), dtype=torch.uint8, device=x.device)
+    _count(1)
+    _lib.check(_lib.lib().pf_tensor_to_image(_vp(x), _vp(out), C.c_longlong(n), Cc, H, W, _st()))
+    return out
+
+
 def timestep_embed(t: Tensor, dim: int, dtype: torch.dtype) -> Tensor:
     n = t.numel()
     out = torch.empty((n, dim), dtype=dtype, device=t.device)

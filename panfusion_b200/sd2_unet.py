@@ -187,3 +187,76 @@ def build_synthetic_controlnet(config: dict | None = None, seed: int = 0, device
         net = SD2ControlNetParams(**config)
     torch.random.set_rng_state(gens)
     return net.eval()
+
+
+# ---- VAE decoder (image-space tail of the loop) ------------------------------------------
+
+SD2_VAE_CONFIG = dict(latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                      norm_num_groups=32, scaling_factor=0.18215)
+
+
+def _vae_resnet(cin, cout, groups):
+    r = _Holder()
+    r.in_channels, r.out_channels = cin, cout
+    r.norm1 = nn.GroupNorm(groups, cin, eps=1e-6)
+    r.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+    r.norm2 = nn.GroupNorm(groups, cout, eps=1e-6)
+    r.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+    r.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+    return r
+
+
+class SD2VAEDecoderParams(_Holder):
+    """Parameter tree of the decoder half of diffusers `AutoencoderKL` [3P] (`post_quant_conv`, `decoder.*`, state-dict
+    names as in `stabilityai/stable-diffusion-2-base/vae`), consumed by panfusion_b200.vae.VAEDecoder."""
+
+    def __init__(self, latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                 norm_num_groups=32, scaling_factor=0.18215):
+        super().__init__()
+        from types import SimpleNamespace
+        boc, g = tuple(block_out_channels), norm_num_groups
+        self.config = SimpleNamespace(latent_channels=latent_channels, out_channels=out_channels, block_out_channels=boc,
+                                      layers_per_block=layers_per_block, norm_num_groups=g,
+                                      scaling_factor=scaling_factor)
+        self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
+        d = _Holder()
+        d.conv_in = nn.Conv2d(latent_channels, boc[-1], 3, padding=1)
+        mid = _Holder()
+        mid.resnets = nn.ModuleList([_vae_resnet(boc[-1], boc[-1], g) for _ in range(2)])
+        att = _Holder()
+        att.heads = 1
+        att.group_norm = nn.GroupNorm(g, boc[-1], eps=1e-6)
+        att.to_q, att.to_k, att.to_v = (nn.Linear(boc[-1], boc[-1]) for _ in range(3))
+        att.to_out = nn.ModuleList([nn.Linear(boc[-1], boc[-1]), nn.Dropout(0.0)])
+        mid.attentions = nn.ModuleList([att])
+        d.mid_block = mid
+        d.up_blocks = nn.ModuleList()
+        rev = boc[::-1]
+        out = rev[0]
+        for i, c in enumerate(rev):
+            prev, out = out, c
+            b = _Holder()
+            b.resnets = nn.ModuleList([_vae_resnet(prev if j == 0 else out, out, g) for j in range(layers_per_block + 1)])
+            b.upsamplers = nn.ModuleList([_sampler(out, 1)]) if i != len(rev) - 1 else None
+            d.up_blocks.append(b)
+        d.conv_norm_out = nn.GroupNorm(g, boc[0], eps=1e-6)
+        d.conv_act = nn.SiLU()
+        d.conv_out = nn.Conv2d(boc[0], out_channels, 3, padding=1)
+        self.decoder = d
+
+    @property
+    def dtype(self):
+        return self.post_quant_conv.weight.dtype
+
+
+def build_synthetic_vae(config: dict | None = None, seed: int = 0, device="cpu") -> SD2VAEDecoderParams:
+    config = config or SD2_VAE_CONFIG
+    dev = torch.device(device)
+    gens = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    if dev.type == "cuda":
+        torch.cuda.manual_seed(seed)
+    with torch.device(dev):
+        net = SD2VAEDecoderParams(**config)
+    torch.random.set_rng_state(gens)
+    return net.eval()

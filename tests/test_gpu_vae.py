@@ -1,0 +1,105 @@
+"""-m gpu: image-space tail of the loop — VAE decode with circular latent padding and
+tensor_to_image through the CUDA path against the oracle (oracle/vae.py: first-party decode_latent / padded panorama
+decode / tensor_to_image restated from PanoGenerator.py:272-278, PanFusion.py:166-172, models/modules/utils.py:9-15;
+the diffusers decoder itself is a [3P] restatement)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_softmax_rows(cuda_device):
+    from panfusion_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for rows, cols, scale in ((37, 192, 0.125), (5, 9216, 512 ** -0.5), (3, 63, 1.0)):
+        s = torch.randn(rows, cols, generator=g) * 8
+        ref = torch.softmax(s * scale, dim=-1)
+        for dt in (torch.float16, torch.bfloat16):
+            out = torch.empty(rows, cols + (cols % 2), dtype=dt, device=cuda_device)[:, :cols]
+            ops.softmax_rows(s.to(cuda_device), out, scale)
+            tol = 1e-3 if dt == torch.float16 else 8e-3
+            torch.testing.assert_close(out.float().cpu(), ref, rtol=tol, atol=1e-6)
+
+
+def test_tensor_to_image_bit_exact(cuda_device):
+    from oracle import vae as ov
+    from panfusion_b200.vae import tensor_to_image
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 3, 3, 20, 36, generator=g) * 0.8
+    # exact ties of (x/2+0.5)*255 at k+0.5 exercise round-half-to-even, plus out-of-range values
+    ties = (torch.arange(0, 255, dtype=torch.float32) + 0.5) / 255 * 2 - 1
+    x.view(-1)[:255] = ties
+    x.view(-1)[255:259] = torch.tensor([-1.5, 1.5, -1.0, 1.0])
+    ref = ov.tensor_to_image(x)
+    got = tensor_to_image(x.to(cuda_device))
+    assert got.dtype == np.uint8 and got.shape == ref.shape == (2, 3, 20, 36, 3)
+    assert np.array_equal(got, ref)
+    u8 = torch.randint(0, 255, (2, 3, 4, 5), dtype=torch.uint8)
+    assert np.array_equal(tensor_to_image(u8), ov.tensor_to_image(u8))
+
+
+def _pair(cuda_device, cfg, dtype):
+    from oracle import vae as ov
+    from panfusion_b200.vae import VAEDecoder
+    orc = ov.build_vae(cfg)
+    return orc, VAEDecoder(orc, compute_dtype=dtype).prepare(cuda_device, dtype)
+
+
+def _cmp(name, got, ref, dtype):
+    scale = ref.abs().max().item()
+    d = (got.float().cpu() - ref).abs()
+    mx, mean = d.max().item() / scale, d.mean().item() / scale
+    lim = (1.5e-2, 2e-3) if dtype == torch.float16 else (8e-2, 1.2e-2)
+    print(f"[parity] {name} {dtype}: max {mx:.3e} mean {mean:.3e} (of max|ref|) limits {lim}")
+    assert mx <= lim[0] and mean <= lim[1]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_vae_decode_tiny_vs_oracle(cuda_device, dtype):
+    """Narrow decoder: raw decode, decode_latent (2 views) and the circularly padded panorama decode + uint8 images."""
+    from oracle import vae as ov
+    from panfusion_b200 import vae as pv
+    orc, mine = _pair(cuda_device, ov.TINY_VAE_CONFIG, dtype)
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(2, 4, 8, 8, generator=g)
+    with torch.no_grad():
+        ref = orc.decode(z).sample
+    _cmp("vae.decode tiny", mine.decode(z.to(cuda_device)), ref, dtype)
+    lat = torch.randn(1, 2, 4, 8, 8, generator=g) * 0.18215 * 4
+    pano = torch.randn(1, 1, 4, 8, 16, generator=g) * 0.18215 * 4
+    with torch.no_grad():
+        ref_l, ref_p = ov.decode_latent(lat, orc), ov.decode_pano(pano, orc, 8)
+    got_l, got_p = pv.decode_latent(lat.to(cuda_device), mine), pv.decode_pano(pano.to(cuda_device), mine, 8)
+    assert got_l.shape == ref_l.shape == (1, 2, 3, 64, 64) and got_p.shape == ref_p.shape == (1, 1, 3, 64, 128)
+    _cmp("decode_latent tiny", got_l, ref_l, dtype)
+    _cmp("decode_pano tiny", got_p, ref_p, dtype)
+    img, ref_img = pv.tensor_to_image(got_p), ov.tensor_to_image(ref_p)
+    diff = np.abs(img.astype(np.int32) - ref_img.astype(np.int32))
+    print(f"[parity] uint8 panorama {dtype}: max level diff {diff.max()}, mean {diff.mean():.3f}")
+    assert diff.mean() < (0.5 if dtype == torch.float16 else 2.5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_vae_decode_sd2_width_vs_oracle(cuda_device, dtype):
+    """SD-2 VAE decoder widths (128/256/512/512, attention head of 512) on small latents: 2 views 8x8 + pano 8x16."""
+    from oracle import vae as ov
+    from panfusion_b200 import vae as pv
+    orc, mine = _pair(cuda_device, ov.SD2_VAE_CONFIG, dtype)
+    g = torch.Generator().manual_seed(3)
+    lat = torch.randn(1, 2, 4, 8, 8, generator=g) * 0.18215 * 4
+    pano = torch.randn(1, 1, 4, 8, 16, generator=g) * 0.18215 * 4
+    with torch.no_grad():
+        ref_l, ref_p = ov.decode_latent(lat, orc), ov.decode_pano(pano, orc, 8)
+    _cmp("decode_latent SD-2 width", pv.decode_latent(lat.to(cuda_device), mine), ref_l, dtype)
+    _cmp("decode_pano SD-2 width", pv.decode_pano(pano.to(cuda_device), mine, 8), ref_p, dtype)
+
+
+def test_vae_rejects_cpu_and_odd_attention_size(cuda_device):
+    from oracle import vae as ov
+    from panfusion_b200.vae import VAEDecoder
+    mine = VAEDecoder(ov.build_vae(ov.TINY_VAE_CONFIG), torch.float16)
+    with pytest.raises((ValueError, RuntimeError)):
+        mine.decode(torch.zeros(1, 4, 8, 8))
+    with pytest.raises(NotImplementedError):
+        mine.decode(torch.zeros(1, 4, 6, 6, device=cuda_device))  # 36 tokens: not a multiple of 64

@@ -128,3 +128,24 @@ def test_ddim_schedule_matches_sd2_leading_spacing():
     a_t, a_p = s.alphas_cumprod[981], s.alphas_cumprod[961]
     ref = a_p.sqrt() * (x - (1 - a_t).sqrt() * e) / a_t.sqrt() + (1 - a_p).sqrt() * e
     torch.testing.assert_close(s.step(e, 981, x), ref)
+
+
+def test_oracle_vae_tail_first_party_semantics():
+    """decode_latent / padded panorama decode / tensor_to_image (PanoGenerator.py:272-278, PanFusion.py:166-172,
+    models/modules/utils.py:9-15) around the [3P] decoder restatement: shapes, scaling, circular seam, rounding."""
+    from oracle import vae as ov
+    vae = ov.build_vae(ov.TINY_VAE_CONFIG)
+    g = torch.Generator().manual_seed(0)
+    pano = torch.randn(1, 1, 4, 8, 16, generator=g)
+    with torch.no_grad():
+        img = ov.decode_pano(pano, vae, 8)
+        assert img.shape == (1, 1, 3, 64, 128)
+        # scaling: decode_latent(z) == vae.decode(z / scaling_factor)
+        direct = vae.decode(pano[:, 0] / vae.config.scaling_factor).sample
+        torch.testing.assert_close(ov.decode_latent(pano, vae)[:, 0], direct)
+        # circular padding makes the decode commute with a roll of the latent up to the padded context
+        rolled = ov.decode_pano(torch.roll(pano, 4, dims=-1), vae, 8)
+        assert (torch.roll(img, 32, dims=-1) - rolled).abs().max() < 0.35 * img.abs().max()
+    x = torch.tensor([[[[-1.0, 1.0, 0.0, -7.0, 7.0, 1 / 255]]]])  # 0.0 -> 127.5 -> 128 (half-to-even, torch.round)
+    assert ov.tensor_to_image(x).tolist() == [[[[0], [255], [128], [0], [255], [128]]]]
+    assert sum(p.numel() for p in ov.build_vae().parameters()) == 49490199  # the SD VAE decoder (+ post_quant_conv)
