@@ -186,6 +186,31 @@ class PanFusionSampler:
         lat, pano = self.finish(rotate_back)
         return lat.to(latents.dtype), pano.to(pano_latent.dtype)
 
+    # ---- PanFusion.inference (PanFusion.py:125-172) after the text encoder ---------------------------------
+    @torch.no_grad()
+    def inference(self, cameras, prompt_embd, pano_prompt_embd, vae, pano_hw, pers_hw, device="cuda", generator=None,
+                  pano_noise: Optional[Tensor] = None, pano_layout_cond: Optional[Tensor] = None, latent_pad: int = 8,
+                  num_steps: Optional[int] = None):
+        """init_noise -> the denoising loop -> rotate back -> VAE decode (views: plain; panorama: circularly padded
+        latent, PanFusion.py:166-172) -> tensor_to_image. Returns (images uint8 [1, m, h, w, 3], pano uint8
+        [1, 1, H, W, 3]) like the reference. `vae` is a panfusion_b200.vae.VAEDecoder; prompt embeddings are the CFG
+        concatenations [null; text] (the CLIP text encoder is outside this path). `pano_noise` [1, 1, 4, H/8, W/8]
+        overrides the random draw (the view noise is always its e2p-nearest resampling)."""
+        from . import vae as pv
+        if pano_noise is None:
+            pano_noise, noise = self.init_noise(1, *pano_hw, *pers_hw, cameras, device, generator)
+        else:
+            cams = {k: v.flatten(0, 1) for k, v in cameras.items()}
+            m = len(cams["FoV"])
+            pano_noise = pano_noise.to(device)
+            rep = pano_noise.expand(-1, m, -1, -1, -1).flatten(0, 1).contiguous()
+            noise = geometry.e2p(rep, cams["FoV"], cams["theta"], cams["phi"], tuple(pers_hw), mode="nearest")[None]
+        lat, pano = self.denoise(noise, pano_noise, prompt_embd.to(device), pano_prompt_embd.to(device), cameras,
+                                 num_steps=num_steps, pano_layout_cond=pano_layout_cond)
+        images = pv.tensor_to_image(pv.decode_latent(lat, vae))
+        pano_img = pv.tensor_to_image(pv.decode_pano(pano, vae, latent_pad))
+        return images, pano_img
+
     def _run_step(self, st, cameras):
         if not self.use_cuda_graph:
             l0 = ops.LAUNCHES
