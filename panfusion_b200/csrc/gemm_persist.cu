@@ -277,17 +277,20 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tmem_ld16(taddr_row + HALF_N + c, vg);
               tmem_ld_wait();
               if (valid) {
-                float o[16];
+                float o[16], ba[16], bg[16];
+                if (p.bias) {  // HALF_N and c are multiples of 16: 128-bit shared-memory loads
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  float a = __uint_as_float(va[e]);
-                  float gt = __uint_as_float(vg[e]);
-                  if (p.bias) {
-                    a += bias_s[c + e];
-                    gt += bias_s[HALF_N + c + e];
+                  for (int e = 0; e < 4; ++e) {
+                    *reinterpret_cast<float4*>(ba + 4 * e) = *reinterpret_cast<const float4*>(bias_s + c + 4 * e);
+                    *reinterpret_cast<float4*>(bg + 4 * e) = *reinterpret_cast<const float4*>(bias_s + HALF_N + c + 4 * e);
                   }
-                  o[e] = a * gelu_erf_f(gt);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) ba[e] = bg[e] = 0.f;
                 }
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                  o[e] = (__uint_as_float(va[e]) + ba[e]) * gelu_erf_f(__uint_as_float(vg[e]) + bg[e]);
                 if (p.out_f32) {
                   float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.out_ld + on0 + c);
 #pragma unroll

@@ -323,21 +323,39 @@ __device__ __forceinline__ float2 unpack2(uint32_t w) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+// MUFU wrappers without the denormal range fix-ups nvcc wraps around expf / division (2 FSETP + FSEL + 3 FMUL per
+// call — the GEGLU epilogue was issue-bound on them, profiles/gemm_geglu_r01_summary.txt): results feed 16-bit stores.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x * sigmoid(x): FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL (relative error ~3e-7)
+__device__ __forceinline__ float silu_f(float x) {
+  return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
+}
 // exact-erf GELU (F.gelu default) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7 + MUFU round-off,
-// three orders of magnitude below one 16-bit output ulp): 1 MUFU.RCP + 1 MUFU.EX2 + ~9 FMA instead of erff()'s
+// three orders of magnitude below one 16-bit output ulp): 2 MUFU + 7 FFMA + 5 FMUL + 1 LOP3 instead of erff()'s
 // branchy ~30-instruction sequence — the GEGLU epilogue evaluates it 80x per thread per tile.
 __device__ __forceinline__ float erf_as_f(float x) {
   const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float r = fmaf(-p * t, __expf(-ax * ax), 1.0f);
+  const float r = fmaf(-p * t, ex2_approx(ax * (ax * -1.4426950408889634f)), 1.0f);
   return copysignf(r, x);
 }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as_f(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf_f(float x) {
+  const float hx = 0.5f * x;
+  return fmaf(hx, erf_as_f(x * 0.70710678118654752440f), hx);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
