@@ -337,7 +337,10 @@ def micro_rooflines(dev, pk):
     alg = x.numel() * 4 + 16 * 2048 * 32 * 32 * 4
     res["e2p_fp32_16x2048x32x64"] = {"bound": "hbm", "ms": round(ms, 4), "algorithmic_bytes": alg,
                                      "achieved": round(alg / ms / 1e6, 1), "peak": pk["hbm"], "unit": "GB/s",
-                                     "frac": round(alg / ms / 1e6 / pk["hbm"], 4)}
+                                     "frac": round(alg / ms / 1e6 / pk["hbm"], 4),
+                                     # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this
+                                     # exact launch (profiles/resample_r01_summary.txt): below the algorithmic bytes, no re-reads
+                                     "traffic": 268.5e6 + 92.4e6, "traffic_source": "profiles/resample_r01_summary.txt"}
     del x
     # (2) tap-GEMM as the dominant 3x3 conv: 16 x 64x64 images, 320 -> 320 channels
     N, H, W, Ci, Co = 16, 64, 64, 320, 320
