@@ -26,6 +26,12 @@ def _cams3():
                 phi=torch.tensor([0.0, 30.0, -60.0]))
 
 
+def _cams_ico():
+    """One camera from each icosahedron ring (utils/pano.py:34-71), degrees."""
+    return dict(FoV=torch.full((4,), 90.0), theta=torch.tensor([-144.0, 72.0, -180.0, 36.0]),
+                phi=torch.tensor([52.6226, 10.8123, -10.8123, -52.6226]))
+
+
 def _report(name, ref, mine):
     err = max((a - b).abs().max().item() for a, b in zip(ref, mine))
     print(f"  {name}: max |oracle - reference| = {err:.3e}")
@@ -65,6 +71,16 @@ def main():
     worst = max(worst, _report("get_masks", [pm, em], oe.get_masks(8, 8, 8, 16, c)))
     worst = max(worst, _report("get_coords", [pc, ec], oe.get_coords(8, 8, 8, 16, c)))
     np.savez_compressed(OUT / "eppa_geometry.npz", pers_masks=pm.numpy(), equi_masks=em.numpy(),
+                        pers_coords=pc.numpy(), equi_coords=ec.numpy())
+
+    # 2b. BASELINE config 4's geometry: pers level smaller than the pano level (ph != eh), icosahedron-ring cameras
+    # (utils/pano.py:34-71: phi = +-52.62 / +-10.81 deg, negative thetas)
+    ci = _cams_ico()
+    pm, em = ref.get_masks(8, 8, 16, 32, ci, "cpu")
+    pc, ec = ref.get_coords(8, 8, 16, 32, ci, "cpu")
+    worst = max(worst, _report("get_masks (ico, ph != eh)", [pm, em], oe.get_masks(8, 8, 16, 32, ci)))
+    worst = max(worst, _report("get_coords (ico, ph != eh)", [pc, ec], oe.get_coords(8, 8, 16, 32, ci)))
+    np.savez_compressed(OUT / "eppa_geometry_c4.npz", pers_masks=pm.numpy(), equi_masks=em.numpy(),
                         pers_coords=pc.numpy(), equi_coords=ec.numpy())
 
     # 3. WarpAttn (models/pano/modules.py:8-59), dim 320, 2 batches x 2 views

@@ -181,6 +181,32 @@ def test_eppa_tables_vs_oracle(cuda_device, ph, pw, eh, ew, V, m):
         torch.testing.assert_close(ge.cpu(), re, rtol=0, atol=5e-6)
 
 
+def test_eppa_tables_vs_reference_goldens(cuda_device):
+    """The CUDA bias tables against the goldens minted by executing the reference's get_masks (not the oracle):
+    the 3-camera rig of tests/golden/eppa_geometry.npz and BASELINE config 4's geometry (ph != eh, icosahedron rings)."""
+    from pathlib import Path
+    import numpy as np
+    from panfusion_b200 import geometry as pg, ops
+    gdir = Path(__file__).parent / "golden"
+    cases = [("eppa_geometry.npz", (8, 8, 8, 16), dict(FoV=torch.tensor([90.0, 75.0, 100.0]),
+                                                       theta=torch.tensor([0.0, 45.0, 200.0]),
+                                                       phi=torch.tensor([0.0, 30.0, -60.0]))),
+             ("eppa_geometry_c4.npz", (8, 8, 16, 32), dict(FoV=torch.full((4,), 90.0),
+                                                           theta=torch.tensor([-144.0, 72.0, -180.0, 36.0]),
+                                                           phi=torch.tensor([52.6226, 10.8123, -10.8123, -52.6226])))]
+    for fname, (ph, pw, eh, ew), cams in cases:
+        gold = np.load(gdir / fname)
+        V, P, E = len(cams["FoV"]), ph * pw, eh * ew
+        pm, em = torch.from_numpy(gold["pers_masks"]), torch.from_numpy(gold["equi_masks"])
+        ref1 = pm.reshape(1, V, E, P).permute(0, 2, 1, 3).reshape(1, E, V * P)   # modules.py:46
+        ref2 = em.reshape(1, V * P, E)                                           # modules.py:53
+        ce, _ = pg.camera_records("e2p", cams["FoV"], cams["theta"], cams["phi"], V, ph, pw, cuda_device)
+        cp, _ = pg.camera_records("p2e", cams["FoV"], cams["theta"], cams["phi"], V, ph, pw, cuda_device)
+        b1, b2 = ops.eppa_tables(ce, cp, V, ph, pw, eh, ew)
+        torch.testing.assert_close(b1.cpu(), ref1, rtol=1e-5, atol=2e-6)
+        torch.testing.assert_close(b2.cpu(), ref2, rtol=1e-5, atol=2e-6)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.uint8])
 def test_pad_pano_bit_exact(cuda_device, dtype):
     """pad_pano / unpad_pano (utils/pano.py:74-105): 4-D and 5-D, every dtype width, against the oracle restatement

@@ -44,6 +44,19 @@ def test_eppa_geometry_matches_reference_golden():
     assert pm.min() >= -1 and pm.max() <= 1 and em.max() == 1.0
 
 
+def test_eppa_geometry_config4_matches_reference_golden():
+    """ph != eh and icosahedron-ring cameras (BASELINE config 4's rig): golden from the reference's get_masks/get_coords."""
+    gold = np.load(GOLD / "eppa_geometry_c4.npz")
+    c = dict(FoV=torch.full((4,), 90.0), theta=torch.tensor([-144.0, 72.0, -180.0, 36.0]),
+             phi=torch.tensor([52.6226, 10.8123, -10.8123, -52.6226]))
+    pm, em = oe.get_masks(8, 8, 16, 32, c)
+    pc, ec = oe.get_coords(8, 8, 16, 32, c)
+    np.testing.assert_allclose(pm.numpy(), gold["pers_masks"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(em.numpy(), gold["equi_masks"], rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(pc.numpy(), gold["pers_coords"])
+    np.testing.assert_array_equal(ec.numpy(), gold["equi_coords"])
+
+
 def test_mask_edge_cases():
     """Camera looking at the pole / FoV so narrow that many queries have no correspondence: rows stay -1."""
     c = dict(FoV=torch.tensor([30.0]), theta=torch.tensor([10.0]), phi=torch.tensor([85.0]))
