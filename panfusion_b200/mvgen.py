@@ -59,6 +59,8 @@ class MultiViewBaseModel(nn.Module):
     def prepare(self, device=None, dtype=None) -> "MultiViewBaseModel":
         """Pack all weights for the kernels (call again after loading new weights)."""
         device = torch.device(device or "cuda")
+        if device.type == "cuda" and device.index is None:  # "cuda" != "cuda:0": would re-pack on every forward
+            device = torch.device("cuda", torch.cuda.current_device())
         dtype = dtype or self.compute_dtype
         _lib.check(_lib.lib().pf_check_device())
         pers = Branch(UNetPack(self.unet, device, dtype), circular=False) if self.unet is not None else None

@@ -137,6 +137,8 @@ class VAEDecoder:
 
     def prepare(self, device=None, dtype=None) -> "VAEDecoder":
         device = torch.device(device or "cuda")
+        if device.type == "cuda" and device.index is None:  # "cuda" != "cuda:0": would re-pack on every decode
+            device = torch.device("cuda", torch.cuda.current_device())
         _lib.check(_lib.lib().pf_check_device())
         self._b = _DecoderBranch(VAEDecoderPack(self.vae, device, dtype or self.compute_dtype))
         return self
