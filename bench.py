@@ -248,6 +248,8 @@ def run_b200(args):
         st["pano"].copy_(h_pano, non_blocking=True)
         st["prompt"].copy_(h_prompt, non_blocking=True)
         st["pano_prompt"].copy_(h_pano_prompt, non_blocking=True)
+        st["timestep"].copy_(h_ts, non_blocking=True)
+        model.update_text(st["prompt"], st["pano_prompt"])  # a prompt that arrives from the host is projected again
         sampler.step(i % n_sched)
         h_out_lat.copy_(st["latents"], non_blocking=True)
         h_out_pano.copy_(st["pano"], non_blocking=True)
@@ -299,6 +301,8 @@ def run_b200(args):
         }
         if not args.skip_micro:
             out["kernels"] = micro_rooflines(dev, pk)
+        if world == 1 and not args.skip_image and not wl.get("layout_cond"):
+            out["image_latency"] = image_latency(model, inp, wl, dev)
         if world == 1 and not args.skip_cpu:
             out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=args.cpu_budget)
     if world > 1:
@@ -308,62 +312,127 @@ def run_b200(args):
         print(json.dumps(out))
 
 
+def _ncu_traffic():
+    """DRAM bytes per launch of the resampling kernels from the committed `ncu --set full` captures
+    (profiles/resample_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); absent -> null."""
+    f = ROOT / "profiles" / "resample_traffic.json"
+    return json.loads(f.read_text()) if f.exists() else {}
+
+
 def micro_rooflines(dev, pk):
-    """Isolated timings of the two kernels the north star names, CUDA events on the launching stream, inputs > L2."""
+    """Isolated timings of the kernels the north star names. Each kernel is launched 20x inside ONE captured CUDA
+    graph (no Python between launches), timed with CUDA events around graph replays; the launches rotate over
+    enough distinct input/output buffers that consecutive launches never touch the same bytes within 126 MB of L2."""
     import numpy as np
     from panfusion_b200 import geometry, ops
     from panfusion_b200.engine import taps3x3
     from panfusion_b200.packing import pack_conv3x3
     res = {}
+    traffic = _ncu_traffic()
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
-    def timeit(fn, iters=20, warm=3):
-        for _ in range(warm):
-            fn()
+    def timeit(fns, launches=20, reps=5):
+        """fns: list of closures over DISTINCT buffers; launch i runs fns[i % len(fns)]. -> ms per launch."""
+        for f in fns:
+            f()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(launches):
+                fns[i % len(fns)]()
+        g.replay()
         torch.cuda.synchronize()
         a, b = ev(), ev()
         a.record()
-        for _ in range(iters):
-            fn()
+        for _ in range(reps):
+            g.replay()
         b.record()
         torch.cuda.synchronize()
-        return a.elapsed_time(b) / iters
+        return a.elapsed_time(b) / (reps * launches)
 
+    def hbm_entry(name, ms, alg, note):
+        t = traffic.get(name)
+        res[name] = {"bound": "hbm", "ms": round(ms, 4), "algorithmic_bytes": alg, "achieved": round(alg / ms / 1e6, 1),
+                     "peak": pk["hbm"], "unit": "GB/s", "frac": round(alg / ms / 1e6 / pk["hbm"], 4),
+                     "traffic": t["dram_bytes"] if t else None, "traffic_source": t["source"] if t else None,
+                     "shape": note}
+
+    th16 = torch.tensor(np.tile(np.arange(8) * 45.0, 2), dtype=torch.float32)
+    fov16, phi16 = torch.full((16,), 90.0), torch.zeros(16)
     # (1) e2p at the reference's own hot-path shape (get_masks, level 32): fp32 (16,2048,32,64) -> (16,2048,32,32)
-    x = torch.randn(16, 2048, 32, 64, device=dev)
-    th = torch.tensor(np.tile(np.arange(8) * 45.0, 2), dtype=torch.float32)
-    fov, phi = torch.full((16,), 90.0), torch.zeros(16)
-    ms = timeit(lambda: geometry.e2p(x, fov, th, phi, (32, 32)))
-    alg = x.numel() * 4 + 16 * 2048 * 32 * 32 * 4
-    res["e2p_fp32_16x2048x32x64"] = {"bound": "hbm", "ms": round(ms, 4), "algorithmic_bytes": alg,
-                                     "achieved": round(alg / ms / 1e6, 1), "peak": pk["hbm"], "unit": "GB/s",
-                                     "frac": round(alg / ms / 1e6 / pk["hbm"], 4),
-                                     # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this
-                                     # exact launch (profiles/resample_r01_summary.txt): below the algorithmic bytes, no re-reads
-                                     "traffic": 268.5e6 + 92.4e6, "traffic_source": "profiles/resample_r01_summary.txt"}
-    del x
-    # (2) tap-GEMM as the dominant 3x3 conv: 16 x 64x64 images, 320 -> 320 channels
+    xs = [torch.randn(16, 2048, 32, 64, device=dev) for _ in range(2)]      # 268 MB each: > L2
+    ms = timeit([(lambda x=x: geometry.e2p(x, fov16, th16, phi16, (32, 32))) for x in xs])
+    hbm_entry("e2p_fp32_16x2048x32x64", ms, xs[0].numel() * 4 + 16 * 2048 * 32 * 32 * 4,
+              "fp32 (16,2048,32,64) -> (16,2048,32,32), SURVEY 8d (i)")
+    del xs
+    # (2) p2e at the reference's hot-path shape: fp32 (16,1024,32,32) -> (16,1024,32,64) + 1 B/px mask
+    ys = [torch.randn(16, 1024, 32, 32, device=dev) for _ in range(3)]      # 67 MB in + 134 MB out per launch
+    ms = timeit([(lambda y=y: geometry.p2e(y, fov16, th16, phi16, (32, 64))) for y in ys])
+    hbm_entry("p2e_fp32_16x1024x32x32", ms, ys[0].numel() * 4 + 16 * 1024 * 32 * 64 * 4 + 16 * 32 * 64,
+              "fp32 (16,1024,32,32) -> (16,1024,32,64) + mask, SURVEY 8d (i)")
+    del ys
+    # (3) feature-map warp, bf16: pano (2,320,64,128) -> 16 views (16,320,64,64); the 2 panoramas are each read by their
+    # 8 views (algorithmic source bytes = the 2 unique panoramas)
+    zs = [torch.randn(2, 320, 64, 128, device=dev).bfloat16() for _ in range(8)]
+    zs = [z.repeat_interleave(8, 0) for z in zs]                              # e2p's signature: one source per camera
+    ms = timeit([(lambda z=z: geometry.e2p(z, fov16, th16, phi16, (64, 64))) for z in zs])
+    hbm_entry("e2p_bf16_2x320x64x128_to_16x320x64x64", ms, 2 * 320 * 64 * 128 * 2 + 16 * 320 * 64 * 64 * 2,
+              "bf16 (2,320,64,128) -> (16,320,64,64), SURVEY 8d (ii)")
+    del zs
+    torch.cuda.empty_cache()
+    # (4) tap-GEMM as the dominant 3x3 conv: 16 x 64x64 images, 320 -> 320 channels
     N, H, W, Ci, Co = 16, 64, 64, 320, 320
     Hp, Wp = H + 2, W + 2
-    a = torch.randn(N * Hp * Wp, Ci, device=dev).bfloat16()
+    As = [torch.randn(N * Hp * Wp, Ci, device=dev).bfloat16() for _ in range(4)]   # 4 x (45 MB in + 42 MB out)
     wgt = pack_conv3x3(torch.randn(Co, Ci, 3, 3) * 0.02).bfloat16().to(dev)
-    o = torch.empty(N * H * W, Co, dtype=torch.bfloat16, device=dev)
-    ms = timeit(lambda: ops.gemm_taps(a, wgt, o, M=N * Hp * Wp, Kc=Ci, taps=taps3x3(Wp), image_map=(Hp, Wp, 1, 1, H, W)))
+    os_ = [torch.empty(N * H * W, Co, dtype=torch.bfloat16, device=dev) for _ in range(4)]
+    ms = timeit([(lambda a=a, o=o: ops.gemm_taps(a, wgt, o, M=N * Hp * Wp, Kc=Ci, taps=taps3x3(Wp),
+                                                 image_map=(Hp, Wp, 1, 1, H, W))) for a, o in zip(As, os_)])
     fl = 2.0 * 9 * Ci * Co * N * H * W
     res["conv3x3_320_16x64x64"] = {"bound": "tensor", "ms": round(ms, 4), "algorithmic_flops": fl,
                                    "achieved": round(fl / ms / 1e9, 1), "peak": pk["tf_burst"], "unit": "TFLOP/s",
                                    "frac": round(fl / ms / 1e9 / pk["tf_burst"], 4)}
-    # (3) flash attention, UNet self-attention at 64x64 (16 images, 5 heads, d 64)
+    del As, os_
+    # (5) flash attention, UNet self-attention at 64x64 (16 images, 5 heads, d 64)
     B, Hh, L, d = 16, 5, 4096, 64
-    qkv = torch.randn(B, L, 3 * Hh * d, device=dev).bfloat16()
-    oo = torch.empty(B, L, Hh * d, dtype=torch.bfloat16, device=dev)
     C = Hh * d
-    ms = timeit(lambda: ops.fmha(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], oo, heads=Hh, head_dim=d, scale=d ** -0.5), iters=10)
+    qs = [torch.randn(B, L, 3 * C, device=dev).bfloat16() for _ in range(3)]       # 3 x (126 MB in + 42 MB out)
+    oo = [torch.empty(B, L, C, dtype=torch.bfloat16, device=dev) for _ in range(3)]
+    ms = timeit([(lambda q=q, o=o: ops.fmha(q[..., :C], q[..., C:2 * C], q[..., 2 * C:], o, heads=Hh, head_dim=d,
+                                            scale=d ** -0.5)) for q, o in zip(qs, oo)], launches=12)
     fl = 4.0 * B * Hh * L * L * d
     res["fmha_d64_16x5x4096"] = {"bound": "tensor", "ms": round(ms, 4), "algorithmic_flops": fl,
                                  "achieved": round(fl / ms / 1e9, 1), "peak": pk["tf_burst"], "unit": "TFLOP/s",
                                  "frac": round(fl / ms / 1e9 / pk["tf_burst"], 4)}
+    del qs, oo
+    torch.cuda.empty_cache()
     return res
+
+
+def image_latency(model, inp, wl, dev, n_steps=50):
+    """What `main.py predict` pays per image (PanFusion.py:125-172 after the text encoder): a FRESH sampler runs
+    init_noise -> 50 denoise steps -> rotate back -> VAE decode (views + circularly padded panorama) -> uint8, wall
+    clock, including the camera-table builds and the 4 CUDA-graph captures of a first image ("cold"); then a second
+    image on the same sampler, which reuses buffers, tables and graphs ("warm")."""
+    from panfusion_b200 import sd2_unet, vae as pv
+    from panfusion_b200.sampler import PanFusionSampler
+    dt = torch.bfloat16
+    dec = pv.VAEDecoder(sd2_unet.build_synthetic_vae(seed=9, device=dev), dt).prepare(dev, dt)
+    sampler = PanFusionSampler(model)
+    prompt, pano_prompt = inp["prompt"].to(dev), inp["pano_prompt"].to(dev)
+    out = {}
+    for tag, seed in (("cold_first_image_s", 11), ("warm_next_image_s", 12)):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        images, pano = sampler.inference(inp["cams"], prompt, pano_prompt, dec, wl["pano_hw"], wl["pers_hw"], device=dev,
+                                         generator=g, num_steps=n_steps)
+        h_img, h_pano = images.cpu(), pano.cpu()
+        out[tag] = round(time.perf_counter() - t0, 4)
+    out["what"] = (f"sampler.inference: init_noise + {n_steps} denoise steps + rotate back + VAE decode of {wl['m']} views "
+                   f"and the padded panorama + tensor_to_image + device->host of the uint8 images")
+    out["image_shapes"] = [list(h_img.shape), list(h_pano.shape)]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -417,65 +486,70 @@ def _oracle_model():
     return _ORACLE_MODEL
 
 
-def _oracle_forward_time(m=2, cfg=False):
-    """Seconds for ONE oracle MultiViewBaseModel.forward (the reference algorithm, fp32, all usable host cores) on
-    `m` views of 64x64 + the 64x128 pano latent; cfg doubles the batch like forward_cls_free does."""
-    from oracle import sampler as osamp
-    torch.set_num_threads(host_threads())
-    model = _oracle_model()
-    g = torch.Generator().manual_seed(0)
-    b = 2 if cfg else 1
-    cams = osamp.horizon_cameras(m, batch=b)
-    pano = torch.randn(b, 1, 4, 64, 128, generator=g)
-    lat = torch.randn(b, m, 4, 64, 64, generator=g)
-    prompt = torch.randn(b, m, 77, 1024, generator=g)
-    pano_prompt = torch.randn(b, 1, 77, 1024, generator=g)
-    ts = torch.full((b, m), 981, dtype=torch.long)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        model(lat, pano, ts, prompt, pano_prompt, cams)
-    return time.perf_counter() - t0
+class _OracleLoop:
+    """The reference's sampling loop (models/pano/PanFusion.py:146-162: rotate -> CFG-batched
+    MultiViewBaseModel.forward -> CFG combine -> 2x DDIM update) on the host cores, through the oracle port, on the
+    benchmark workload itself (same views / latent sizes / CFG batch / cameras / guidance as the B200 arm)."""
 
+    def __init__(self, workload):
+        from oracle import sampler as osamp
+        torch.set_num_threads(host_threads())
+        self.osamp, self.model = osamp, _oracle_model()
+        wl = WORKLOADS[workload]
+        if wl.get("layout_cond"):
+            raise NotImplementedError("CPU arm of the layout-conditioned workload: time c2 (the ControlNet adds 7.5 % FLOPs)")
+        inp = synthetic_inputs(wl, 1024, "cpu", None)
+        self.cams = inp["cams"]
+        self.pano = inp["pano"]
+        self.lat = osamp.init_noise(self.pano, *wl["pers_hw"], self.cams)
+        self.prompt, self.pano_prompt = inp["prompt"], inp["pano_prompt"]
+        self.i = 0
 
-# algorithmic FLOPs of the bounded CPU sample: one un-guided forward with 2 views (BASELINE configs[0], SURVEY App. C)
-FLOPS_SAMPLE = 3.669e12
+    def step(self) -> float:
+        """One iteration of the loop; returns its wall time in seconds."""
+        t0 = time.perf_counter()
+        self.lat, self.pano, self.cams = self.osamp.denoise_steps(
+            self.model, self.lat, self.pano, self.prompt, self.pano_prompt, self.cams, num_steps=1,
+            start_step=self.i % 50)
+        self.i += 1
+        return time.perf_counter() - t0
 
 
 def cpu_baseline(workload, budget_s=30.0):
-    """The reference algorithm (oracle port) on the host cores, on a BOUNDED sample of the workload: one forward of
-    BASELINE configs[0] (1 pano 64x128 + 2 views 64x64, no CFG: 3.67 TFLOP, ~20 s on 8 cores), scaled to the step of
-    the benchmark workload by algorithmic FLOPs. A reported baseline, not a target."""
+    """ONE real iteration of the reference loop on the benchmark workload (oracle port, fp32, all usable host cores):
+    no extrapolation. About a minute of CPU work at C2 — the smallest sample that IS the metric's unit."""
     cores = host_threads()
-    t = _oracle_forward_time(m=2, cfg=False)
-    scale = FLOPS_PER_STEP[workload] / FLOPS_SAMPLE
-    return {"value": round(1.0 / (t * scale), 5), "unit": "steps/s", "cores": cores, "kind": "port",
-            "sample": f"one oracle forward of BASELINE configs[0] (2 views, no CFG, 3.67 TFLOP) took {t:.1f} s on "
-                      f"{cores} threads; scaled x{scale:.2f} by algorithmic FLOPs to the benchmark step"}
+    loop = _OracleLoop(workload)
+    t = loop.step()
+    return {"value": round(1.0 / t, 5), "unit": "steps/s", "cores": cores, "kind": "port",
+            "sample": f"1 full denoise step of this workload (rotate + CFG-batched forward + combine + 2 DDIM updates, "
+                      f"reference algorithm via the oracle port, fp32) = {t:.1f} s on {cores} threads; measured, not scaled"}
 
 
 def run_reference(args):
-    """`--impl reference`: the reference algorithm's CPU path (oracle port; diffusers/xformers/kornia are not
-    installable offline) on the usable host cores. Rank 0 only. Each "step" is the bounded sample of
-    cpu_baseline (one 2-view forward) scaled by algorithmic FLOPs; at most ~4 minutes in total."""
+    """`--impl reference`: the reference algorithm's own CPU path (oracle port; diffusers/xformers/kornia are not
+    installable offline) on the usable host cores, REAL steps of the benchmark workload: one warm-up
+    step, then as many timed steps as fit `--ref-budget` seconds (at least 2, at most --steps). `steps` / `warmup` in
+    the JSON line are the counts actually run. Rank 0 only."""
     if int(os.environ.get("RANK", 0)) != 0:
         return
     wl = WORKLOADS[args.workload]
     cores = host_threads()
-    scale = FLOPS_PER_STEP[args.workload] / FLOPS_SAMPLE
-    t_first = _oracle_forward_time(m=2, cfg=False)  # warm-up (also builds the model)
-    n_timed = max(1, min(args.steps, int(200 / max(t_first, 1e-3))))
-    t0 = time.perf_counter()
-    for _ in range(n_timed):
-        _oracle_forward_time(m=2, cfg=False)
-    per = (time.perf_counter() - t0) / n_timed * scale
+    loop = _OracleLoop(args.workload)
+    t_warm = loop.step()
+    n_timed = max(2, min(args.steps, int(args.ref_budget / max(t_warm, 1e-3))))
+    times = [loop.step() for _ in range(n_timed)]
+    per = sum(times) / n_timed
     val = round(1.0 / per, 5)
-    sample = (f"each step = one oracle forward of BASELINE configs[0] (2 views, no CFG, 3.67 TFLOP; {per / scale:.1f} s on "
-              f"{cores} threads) scaled x{scale:.2f} by algorithmic FLOPs to the benchmark step")
+    sample = (f"{n_timed} full denoise steps of this workload after 1 warm-up step (rotate + CFG-batched forward + combine "
+              f"+ 2 DDIM updates; reference algorithm via the oracle port, fp32, {cores} threads): "
+              f"{', '.join(f'{t:.1f}' for t in times)} s; measured, not scaled")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": n_timed, "warmup": 1, "ms_per_step": round(per * 1e3, 1), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "views": wl["m"], "cfg_batch": 2},
+        "config": {"workload": wl["desc"], "views": wl["m"], "cfg_batch": 2, "pano_latent": list(wl["pano_hw"]),
+                   "view_latent": list(wl["pers_hw"]), "weights": "synthetic SD-2 architecture"},
         "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -491,7 +565,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-micro", action="store_true", help="skip the isolated kernel rooflines")
+    ap.add_argument("--skip-image", action="store_true", help="skip the cold / warm whole-image latency leg")
     ap.add_argument("--cpu-budget", type=float, default=30.0)
+    ap.add_argument("--ref-budget", type=float, default=240.0,
+                    help="--impl reference: seconds of TIMED reference steps (at least 2 steps are always run)")
     ap.add_argument("--profile-one-step", action="store_true", help="for ncu --profile-from-start off: profile one eager step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

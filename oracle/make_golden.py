@@ -2,6 +2,8 @@
 check the oracle restatement against them. Runs only where /root/reference is mounted (the build container).
 
     python -m oracle.make_golden [--full]     # --full adds the SD-2-size C1 step (minutes on 8 cores)
+    python -m oracle.make_golden --only c2    # BASELINE configs[1]: SD-2 widths, 8 views, CFG pair (b = 2)
+    python -m oracle.make_golden --only c4geo # get_masks at config 4's real level size (32x32 views, 64x128 pano)
 
 Each fixture stores the seeded inputs' identifying parameters and the reference outputs; tests regenerate the
 inputs from the seeds (same torch build on both boxes) and compare.
@@ -38,14 +40,62 @@ def _report(name, ref, mine):
     return err
 
 
+def golden_c2(ref):
+    """BASELINE configs[1], the benchmarked configuration: SD-2 widths, 8 horizon views 64x64 + pano 64x128, the CFG
+    pair (b = 2, prompts [null; text]) — ONE reference MultiViewBaseModel.forward (MVGenModel.py:38-297) on CPU."""
+    cfg = ounet.SD2_CONFIG
+    model_r = synth.build_model(ref.MultiViewBaseModel, cfg, seed=0)
+    inp = synth.step_inputs_cfg(8, (64, 128), (64, 64), cfg["cross_attention_dim"], seed=0)
+    t0 = time.time()
+    rs, rp_ = model_r(**inp)
+    t1 = time.time()
+    print(f"  [c2] reference forward {t1 - t0:.1f}s", flush=True)
+    np.savez_compressed(OUT / "mvgen_c2.npz", sample=rs.numpy(), pano_sample=rp_.numpy())
+    model_o = synth.build_model(om.MultiViewBaseModel, cfg, seed=0)
+    model_o.load_state_dict(model_r.state_dict())
+    del model_r
+    os_, op_ = model_o(**inp)
+    print(f"  [c2] oracle forward {time.time() - t1:.1f}s", flush=True)
+    return _report("MultiViewBaseModel c2", [rs, rp_], [os_, op_])
+
+
+C4GEO_LEVEL = (32, 32, 64, 128)   # config 4's first EPPA level: 512^2 views / 8 / 2, 1024x2048 pano / 8 / 2
+
+
+def c4geo_subsample(pm, em):
+    """The full masks are 2 x 134 MB: the fixture keeps every 7th x 9th panorama query row of pers_masks, every 5th x
+    5th view query row of equi_masks (all keys), plus the key-sum of EVERY query row (float64) of both."""
+    return dict(pers_rows=pm[:, ::7, ::9].numpy(), equi_rows=em[:, ::5, ::5].numpy(),
+                pers_rowsum=pm.double().sum((-1, -2)).numpy(), equi_rowsum=em.double().sum((-1, -2)).numpy())
+
+
+def golden_c4_geometry(ref):
+    """get_masks (models/pano/utils.py:10-84) at config 4's REAL first-level size with one camera per icosahedron
+    ring — the sizes at which the circular / replicate blur borders, the pole rows and the per-row normalisation see
+    production-size grids."""
+    ci = _cams_ico()
+    ph, pw, eh, ew = C4GEO_LEVEL
+    t0 = time.time()
+    pm, em = ref.get_masks(ph, pw, eh, ew, ci, "cpu")
+    print(f"  [c4geo] reference get_masks {time.time() - t0:.1f}s", flush=True)
+    err = _report("get_masks (ico, 32x32 / 64x128)", [pm, em], oe.get_masks(ph, pw, eh, ew, ci))
+    np.savez_compressed(OUT / "eppa_geometry_c4_level.npz", **c4geo_subsample(pm, em))
+    return err
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
+    ap.add_argument("--only", choices=["c2", "c4geo"], help="mint just one of the large fixtures")
     args = ap.parse_args()
     ref = ref_loader.load()
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_grad_enabled(False)
     worst = 0.0
+    if args.only == "c2":
+        return 0 if golden_c2(ref) < 1e-4 else 1
+    if args.only == "c4geo":
+        return 0 if golden_c4_geometry(ref) < 1e-5 else 1
 
     # 1. resampling (e2p.py:54-76, p2e.py:52-77)
     g = torch.Generator().manual_seed(0)

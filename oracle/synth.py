@@ -30,6 +30,22 @@ def step_inputs(m: int, pano_hw, pers_hw, ctx_dim: int, seed: int = 0, batch: in
                 cameras=cams)
 
 
+def step_inputs_cfg(m: int, pano_hw, pers_hw, ctx_dim: int, seed: int = 0, t: int = 981):
+    """Inputs of the CFG-batched forward exactly as PanFusion.forward_cls_free hands them to the denoiser
+    (PanFusion.py:100-108, PanoGenerator.py:240-251): every input duplicated along the batch, prompts = [null; text]
+    (PanFusion.py:135-138), cameras duplicated. b = 2, m views (BASELINE configs[1] for m = 8)."""
+    g = torch.Generator().manual_seed(seed)
+    cams = sampler.horizon_cameras(m, batch=1)
+    pano = torch.randn(1, 1, 4, *pano_hw, generator=g)
+    lat = sampler.init_noise(pano, pers_hw[0], pers_hw[1], cams)
+    text = torch.randn(1, 1, 77, ctx_dim, generator=g)
+    null = torch.randn(1, 1, 77, ctx_dim, generator=g)
+    dup = lambda x: torch.cat([x] * 2)
+    return dict(latents=dup(lat), pano_latent=dup(pano), timestep=torch.full((2, m), t, dtype=torch.long),
+                prompt_embd=torch.cat([null.repeat(1, m, 1, 1), text.repeat(1, m, 1, 1)]),
+                pano_prompt_embd=torch.cat([null, text]), cameras={k: dup(v) for k, v in cams.items()})
+
+
 def build_model(model_cls, config=None, seed: int = 0):
     """Two independently seeded UNets + the EPPA blocks with their zero-init tensors redrawn."""
     config = config or ounet.SD2_CONFIG

@@ -60,9 +60,19 @@ def load_reference_state_dict(model, state_dict: Mapping[str, Tensor], prefix: s
     report {'loaded', 'folded', 'missing', 'unexpected'}; with strict=True missing / unexpected names raise like
     `nn.Module.load_state_dict`. The packed kernel weights are invalidated (re-packed on the next forward)."""
     plain, lora = split_reference_state_dict(state_dict, prefix)
-    own = dict(model.state_dict())
+    # the user's own UNets may be torch.compile'd as well: map clean names to the model's tensors
+    own = {k.replace("_orig_mod.", ""): v for k, v in model.state_dict().items()}
     unexpected = sorted(k for k in plain if k not in own)
     missing = sorted(k for k in own if k not in plain)
+    if not any(k in own for k in plain) and not any(t in own for t in lora):
+        # nothing matched: wrong prefix (e.g. a state_dict saved without 'mv_base_model.') — never a silent no-op
+        raise KeyError(f"no key of the checkpoint matches the model under prefix {prefix!r} "
+                       f"(first keys: {list(state_dict)[:3]})")
+    if lora and not plain:
+        # a LoRA-only checkpoint folds into whatever base weights the model holds: folding it twice is silently wrong
+        if getattr(model, "_lora_folded", False):
+            raise RuntimeError("LoRA adapters were already folded into this model's weights; reload the base weights "
+                               "before loading a LoRA-only checkpoint again")
     for name, value in plain.items():
         if name in own:
             if own[name].shape != value.shape:
@@ -76,6 +86,13 @@ def load_reference_state_dict(model, state_dict: Mapping[str, Tensor], prefix: s
         own[target].copy_(fold_lora(own[target], parts["down"].to(own[target].device), parts["up"].to(own[target].device),
                                     lora_scale))
         folded += 1
+    if lora:
+        model._lora_folded = True
+    non_lora_missing = [k for k in missing if "cp_blocks" in k]
+    if non_lora_missing and not strict:
+        import warnings
+        warnings.warn(f"{len(non_lora_missing)} EPPA (cp_blocks) tensors are not in the checkpoint and keep their current "
+                      f"values, e.g. {non_lora_missing[:3]}", stacklevel=2)
     if strict and (missing or unexpected):
         raise RuntimeError(f"missing keys: {missing[:8]}{'...' if len(missing) > 8 else ''}; "
                            f"unexpected keys: {unexpected[:8]}{'...' if len(unexpected) > 8 else ''}")
@@ -85,7 +102,14 @@ def load_reference_state_dict(model, state_dict: Mapping[str, Tensor], prefix: s
                 unexpected=sorted(unexpected))
 
 
-def load_reference_checkpoint(model, path: str, map_location="cpu", **kw) -> dict:
-    """`torch.load(path)['state_dict']` (PanoGenerator.py:88) -> load_reference_state_dict."""
-    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+def load_reference_checkpoint(model, path: str, map_location="cpu", allow_pickle: bool = False, **kw) -> dict:
+    """`torch.load(path)['state_dict']` (PanoGenerator.py:88) -> load_reference_state_dict. Only tensors are needed, so
+    the file is read with `weights_only=True`; Lightning checkpoints that carry pickled hyper-parameter objects need
+    `allow_pickle=True` (arbitrary code execution from an untrusted file — opt in explicitly)."""
+    try:
+        ckpt = torch.load(path, map_location=map_location, weights_only=True)
+    except Exception:
+        if not allow_pickle:
+            raise
+        ckpt = torch.load(path, map_location=map_location, weights_only=False)
     return load_reference_state_dict(model, ckpt["state_dict"] if "state_dict" in ckpt else ckpt, **kw)

@@ -207,7 +207,11 @@ class Branch:
         p = self.p
         n, L, ctx = prompt.shape
         x = prompt.reshape(n * L, ctx).to(self.dt).contiguous()
-        kv = torch.empty((n * L, p.kv_all.n), dtype=self.dt, device=p.dev)
+        # a new text of the same shape is projected INTO the existing buffer: captured CUDA graphs read it by address
+        if self.text_kv is not None and tuple(self.text_kv.shape) == (n, L, p.kv_all.n):
+            kv = self.text_kv.reshape(n * L, p.kv_all.n)
+        else:
+            kv = torch.empty((n * L, p.kv_all.n), dtype=self.dt, device=p.dev)
         ops.gemm_taps(x, p.kv_all.w, kv, M=n * L, Kc=ctx)
         self.text_kv = kv.reshape(n, L, p.kv_all.n)
         self._text_key = key

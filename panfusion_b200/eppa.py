@@ -68,10 +68,58 @@ class CameraTables:
     rotation per step (PanFusion.py:114-123) cycles through a handful of camera sets, and the two CFG halves carry
     identical cameras (PanoGenerator.py:245-246), so after the first few steps every lookup hits."""
 
-    def __init__(self):
+    def __init__(self, max_camera_sets: int = 16):
+        """max_camera_sets bounds the cache (LRU over camera sets; the fixed predict rig needs 4 — one per rotation
+        phase): random rigs (train-mode cam_rot / random_sample_camera, a rot_diff that does not divide 360) would
+        otherwise grow device memory without limit (~35-143 MB per set at SD-2 size). Evicted tables stay alive for as
+        long as a captured CUDA graph holds them (`tensors_of`)."""
         self._bias = {}
         self._pe = {}
         self._rec = {}
+        self.max_camera_sets = max_camera_sets
+        self._lru: list = []   # camera keys, least recently used first
+
+    def _touch(self, key) -> None:
+        if self._lru and self._lru[-1] == key:
+            return
+        if key in self._lru:
+            self._lru.remove(key)
+        self._lru.append(key)
+        while len(self._lru) > self.max_camera_sets:
+            old = self._lru.pop(0)
+            for cache in (self._bias, self._pe, self._rec):
+                for k in [k for k in cache if self._key_of(k) == old]:
+                    del cache[k]
+
+    @staticmethod
+    def _key_of(cache_key):
+        return cache_key[2] if cache_key[0] == "local" else cache_key[0]
+
+    def tensors_of(self, key) -> list:
+        """Every cached tensor that belongs to camera set `key` (to be held by whoever captured their addresses)."""
+        key = self.dedup_any(key)
+        out = []
+        for cache in (self._bias, self._pe, self._rec):
+            for k, v in cache.items():
+                if self._key_of(k) in key:
+                    out.extend(t for t in (v if isinstance(v, (tuple, list)) else (v,)) if torch.is_tensor(t))
+        return out
+
+    @staticmethod
+    def dedup_any(key) -> tuple:
+        """The camera keys a full (b*m)-camera key can be stored under: itself and every per-batch-element group."""
+        n = len(key[0])
+        keys = {key}
+        for b in range(1, n + 1):
+            if n % b == 0:
+                keys.add(CameraTables.dedup(key, b)[0])
+        return tuple(keys)
+
+    def clear(self) -> None:
+        self._bias.clear()
+        self._pe.clear()
+        self._rec.clear()
+        self._lru.clear()
 
     @staticmethod
     def camera_key(cameras: dict) -> tuple:
@@ -99,6 +147,7 @@ class CameraTables:
 
     def bias(self, key, groups, ph, pw, eh, ew, dev):
         k = (key, groups, ph, pw, eh, ew)
+        self._touch(key)
         if k not in self._bias:
             V = len(key[0])
             ce, cp = self._records(key, V, ph, pw, dev)
@@ -109,6 +158,7 @@ class CameraTables:
 
     def pe(self, key, ph, pw, eh, ew, freq_bands: Tensor, dev):
         k = (key, ph, pw, eh, ew, freq_bands.numel())  # SphericalPE's table is a function of n_freqs only
+        self._touch(key)
         if k not in self._pe:
             ce, _ = self._records(key, len(key[0]), ph, pw, dev)
             self._pe[k] = ops.eppa_pe(ce, ph, pw, eh, ew, freq_bands)
@@ -116,6 +166,8 @@ class CameraTables:
 
 
 class WarpAttn(nn.Module):
+    kv_tap = None  # test hook: called with the local views' projected K|V [b, m_loc*P, 2C] of every forward
+
     def __init__(self, dim):
         super().__init__()
         self.dim = dim
@@ -178,6 +230,8 @@ class WarpAttn(nn.Module):
         qkv_p = ops.gemm_taps(ap, w["qkv"].w, new(Tp, 3 * C), M=Tp, Kc=C).reshape(b, m_loc * P, 3 * C)
         qkv_e = ops.gemm_taps(ae, w["qkv"].w, new(Te, 3 * C), M=Te, Kc=C).reshape(b, E, 3 * C)
         scale = d ** -0.5
+        if WarpAttn.kv_tap is not None:
+            WarpAttn.kv_tap(qkv_p[..., C:])
         if m_loc != m:
             # the one collective of the block: K|V of every view shard (bf16, 2C per token) over NVLink
             kv_loc = new(Tp, 2 * C)

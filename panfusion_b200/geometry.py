@@ -59,14 +59,23 @@ def _scalar(v, i):
     return float(v)
 
 
+def _values(v, n: int) -> tuple:
+    """index_list_or_scalar (utils.py:18-23) for i in range(n), with ONE host read per argument (a tensor argument
+    costs one .tolist(), not n .item() calls — the launch path of a 70 us kernel must not take longer than the kernel)."""
+    if isinstance(v, Tensor):
+        v = v.detach().reshape(-1).tolist() if v.dim() else float(v)
+    if hasattr(v, "__len__"):
+        return tuple(_scalar(v, i) for i in range(n))
+    return (float(v),) * n
+
+
 def camera_records(kind: str, fov_deg, u_deg, v_deg, batch: int, h: int, w: int, device) -> tuple[Tensor, int]:
     """-> (records[n, 20] float64 on device, cam_stride). All-scalar cameras broadcast (e2p.py:65-66)."""
     if all(not hasattr(v, "__len__") for v in (fov_deg, u_deg, v_deg)):
         n, stride = 1, 0
     else:
         n, stride = batch, 1
-    key = (kind, tuple(_scalar(fov_deg, i) for i in range(n)), tuple(_scalar(u_deg, i) for i in range(n)),
-           tuple(_scalar(v_deg, i) for i in range(n)), int(h), int(w), str(device))
+    key = (kind, _values(fov_deg, n), _values(u_deg, n), _values(v_deg, n), int(h), int(w), str(device))
     t = _RECORD_CACHE.get(key)
     if t is None:
         recs = [_camera_record(kind, key[1][i], key[2][i], key[3][i], int(h), int(w)) for i in range(n)]

@@ -77,6 +77,27 @@ class MultiViewBaseModel(nn.Module):
     def invalidate(self):
         self._branches = None
 
+    @torch.no_grad()
+    def update_text(self, prompt_embd: Optional[Tensor], pano_prompt_embd: Tensor) -> None:
+        """Re-project the text K/V of both branches for new prompt embeddings of the SAME shapes, into the buffers the
+        previous call used. A captured CUDA graph of `forward` does not contain the (cached) text projection; the
+        sampler calls this when it reuses its graphs for a new prompt (PanFusion.py:134-138 embeds once per image)."""
+        if self._branches is None:
+            return
+        pers, pano, dev, dt = self._branches
+        tkey = lambda t, tag: (t.data_ptr(), t._version, tuple(t.shape), tag)
+        par = self._par if pers is not None else None
+        text_key = tkey(prompt_embd, "pers") if prompt_embd is not None else None
+        pano_text_key = tkey(pano_prompt_embd, "pano")
+        if par is not None:
+            b_full, m_full = prompt_embd.shape[:2]
+            par.configure(b_full, m_full)
+            bsl, vsl = par.slices(b_full, m_full)
+            prompt_embd, pano_prompt_embd = prompt_embd[bsl, vsl], pano_prompt_embd[bsl]
+        if pers is not None and prompt_embd is not None:
+            pers.set_text(prompt_embd.flatten(0, 1), text_key)
+        pano.set_text(pano_prompt_embd.flatten(0, 1), pano_text_key)
+
     # ---- forward -----------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, latents: Optional[Tensor], pano_latent: Tensor, timestep: Tensor, prompt_embd: Optional[Tensor],

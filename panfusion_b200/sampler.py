@@ -59,8 +59,11 @@ class PanFusionSampler:
         self.scheduler = DDIMSchedule()
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
+        self.max_graphs = 16   # captured steps kept (one per rotation phase and rig); oldest dropped first
         self._pool = None
         self.launches_per_step = None
+        self._st = None
+        self._cond_phases = None
 
     # ---- PanFusion.py:30-43 -------------------------------------------------------------------------
     def init_noise(self, bs, equi_h, equi_w, pers_h, pers_w, cameras, device, generator=None):
@@ -118,37 +121,59 @@ class PanFusionSampler:
         (PanFusion.py:152-153); pers_layout_cond [1, m, 3, 8h, 8w] is passed through unchanged (:103-104)."""
         dev = latents.device
         self.scheduler.set_timesteps(self.diff_timestep)
+        if latents.shape[0] != 1:
+            raise NotImplementedError("PanFusionSampler runs one panorama per call (batch 1, like `main.py predict`); "
+                                      f"got batch {latents.shape[0]}")
         m = latents.shape[1]
         W = pano_latent.shape[-1]
         self._roll = int(self.rot_diff / 360 * W) if self.rot_diff % 360 else 0
-        coefs = torch.tensor([self.scheduler.coefficients(int(t)) for t in self.scheduler.timesteps],
-                             dtype=torch.float32)
-        st = dict(latents=latents.to(torch.float32).contiguous().clone(),
-                  # the rotation of the first step (PanFusion.py:149); later ones are fused into the DDIM kernel
-                  pano=torch.roll(pano_latent.to(torch.float32), self._roll, dims=-1).contiguous(),
-                  timestep=torch.zeros((1, m), dtype=torch.float32, device=dev),
-                  prompt=prompt_embd.contiguous(), pano_prompt=pano_prompt_embd.contiguous(),
-                  coef=torch.zeros(2, dtype=torch.float32, device=dev),
-                  coef_table=coefs.to(dev), ts_table=self.scheduler.timesteps.to(dev, torch.float32))
-        st["latents_next"], st["pano_next"] = torch.empty_like(st["latents"]), torch.empty_like(st["pano"])
         dup = lambda t: torch.cat([t] * 2).contiguous()
-        if pers_layout_cond is not None:
-            st["pers_cond"] = dup(pers_layout_cond.to(dev))
-        self._cond_phases = None
-        if pano_layout_cond is not None:
-            # the rolled conditions repeat with a short period (4 for 90 degrees): keep every phase as its own tensor,
-            # so the ControlNet's conditioning embedding is computed once per phase and cached on the tensor identity
-            Wc = pano_layout_cond.shape[-1]
-            r = int(self.rot_diff / 360 * Wc) % Wc if self.rot_diff % 360 else 0
-            period = Wc // math.gcd(Wc, r) if r else 1
-            if period > 8:
-                raise NotImplementedError(f"layout condition with rot_diff={self.rot_diff}: {period} distinct rolls")
-            self._cond_phases = [dup(torch.roll(pano_layout_cond.to(dev), (k + 1) * r, dims=-1)) for k in range(period)]
-        self._st = st
+        # Static buffers and captured graphs are kept ACROSS calls: a new image of the same shapes copies its inputs into
+        # the existing buffers (the graphs read them by address) and re-projects the text K/V in place. Layout
+        # conditions carry cached ControlNet features bound to tensor identities, so conditioned runs start afresh.
+        sig = (str(dev), tuple(latents.shape), tuple(pano_latent.shape), tuple(prompt_embd.shape),
+               tuple(pano_prompt_embd.shape), self.diff_timestep, self.rot_diff,
+               id(getattr(self.mv_base_model, "_branches", None)))
+        reuse = (getattr(self, "_st", None) is not None and getattr(self, "_sig", None) == sig
+                 and pers_layout_cond is None and pano_layout_cond is None and "pers_cond" not in self._st
+                 and self._cond_phases is None)
+        if reuse:
+            st = self._st
+            st["latents"].copy_(latents)
+            st["pano"].copy_(torch.roll(pano_latent.to(torch.float32), self._roll, dims=-1))
+            st["prompt"].copy_(prompt_embd)
+            st["pano_prompt"].copy_(pano_prompt_embd)
+            if self._graphs:
+                self.mv_base_model.update_text(st["prompt"], st["pano_prompt"])
+        else:
+            coefs = torch.tensor([self.scheduler.coefficients(int(t)) for t in self.scheduler.timesteps],
+                                 dtype=torch.float32)
+            st = dict(latents=latents.to(torch.float32).contiguous().clone(),
+                      # the rotation of the first step (PanFusion.py:149); later ones are fused into the DDIM kernel
+                      pano=torch.roll(pano_latent.to(torch.float32), self._roll, dims=-1).contiguous(),
+                      timestep=torch.zeros((1, m), dtype=torch.float32, device=dev),
+                      prompt=prompt_embd.contiguous().clone(), pano_prompt=pano_prompt_embd.contiguous().clone(),
+                      coef=torch.zeros(2, dtype=torch.float32, device=dev),
+                      coef_table=coefs.to(dev), ts_table=self.scheduler.timesteps.to(dev, torch.float32))
+            st["latents_next"], st["pano_next"] = torch.empty_like(st["latents"]), torch.empty_like(st["pano"])
+            if pers_layout_cond is not None:
+                st["pers_cond"] = dup(pers_layout_cond.to(dev))
+            self._cond_phases = None
+            if pano_layout_cond is not None:
+                # the rolled conditions repeat with a short period (4 for 90 degrees): keep every phase as its own
+                # tensor, so the ControlNet's conditioning embedding is computed once per phase and cached on the
+                # tensor identity
+                Wc = pano_layout_cond.shape[-1]
+                r = int(self.rot_diff / 360 * Wc) % Wc if self.rot_diff % 360 else 0
+                period = Wc // math.gcd(Wc, r) if r else 1
+                if period > 8:
+                    raise NotImplementedError(f"layout condition with rot_diff={self.rot_diff}: {period} distinct rolls")
+                self._cond_phases = [dup(torch.roll(pano_layout_cond.to(dev), (k + 1) * r, dims=-1)) for k in range(period)]
+            self._st, self._sig = st, sig
+            self._graphs = {}
         self._cameras = {k: v.detach().to("cpu", torch.float32) for k, v in cameras.items()}
         self._curr_rot = 0.0
         self._n_rot = 0
-        self._graphs = {}
 
     @torch.no_grad()
     def step(self, i: int) -> None:
@@ -190,10 +215,11 @@ class PanFusionSampler:
     @torch.no_grad()
     def inference(self, cameras, prompt_embd, pano_prompt_embd, vae, pano_hw, pers_hw, device="cuda", generator=None,
                   pano_noise: Optional[Tensor] = None, pano_layout_cond: Optional[Tensor] = None, latent_pad: int = 8,
-                  num_steps: Optional[int] = None):
+                  num_steps: Optional[int] = None, pers_layout_cond: Optional[Tensor] = None):
         """init_noise -> the denoising loop -> rotate back -> VAE decode (views: plain; panorama: circularly padded
         latent, PanFusion.py:166-172) -> tensor_to_image. Returns (images uint8 [1, m, h, w, 3], pano uint8
-        [1, 1, H, W, 3]) like the reference. `vae` is a panfusion_b200.vae.VAEDecoder; prompt embeddings are the CFG
+        [1, 1, H, W, 3]) like the reference. `pers_layout_cond` / `pano_layout_cond` are
+        batch['images_layout_cond'] / batch['pano_layout_cond'] (PanFusion.py:155-157). `vae` is a panfusion_b200.vae.VAEDecoder; prompt embeddings are the CFG
         concatenations [null; text] (the CLIP text encoder is outside this path). `pano_noise` [1, 1, 4, H/8, W/8]
         overrides the random draw (the view noise is always its e2p-nearest resampling)."""
         from . import vae as pv
@@ -206,7 +232,8 @@ class PanFusionSampler:
             rep = pano_noise.expand(-1, m, -1, -1, -1).flatten(0, 1).contiguous()
             noise = geometry.e2p(rep, cams["FoV"], cams["theta"], cams["phi"], tuple(pers_hw), mode="nearest")[None]
         lat, pano = self.denoise(noise, pano_noise, prompt_embd.to(device), pano_prompt_embd.to(device), cameras,
-                                 num_steps=num_steps, pano_layout_cond=pano_layout_cond)
+                                 num_steps=num_steps, pers_layout_cond=pers_layout_cond,
+                                 pano_layout_cond=pano_layout_cond)
         images = pv.tensor_to_image(pv.decode_latent(lat, vae))
         pano_img = pv.tensor_to_image(pv.decode_pano(pano, vae, latent_pad))
         return images, pano_img
@@ -247,6 +274,13 @@ class PanFusionSampler:
                 with torch.cuda.graph(g, pool=self._pool):
                     self._step_body(st, cameras)
             self.launches_per_step = ops.LAUNCHES - l0  # kernels of ours inside one replayed step
+            # the graph reads the camera tables by address: it co-owns them (the table cache is LRU-bounded)
+            tables = getattr(getattr(self.mv_base_model, "cp_blocks_mid", None), "tables", None)
+            if tables is not None:
+                cam2 = {k: torch.cat([v] * 2).flatten(0, 1) for k, v in cameras.items()}
+                g._pf_tables = tables.tensors_of(tables.camera_key(cam2))
+            while len(self._graphs) >= self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = g
             st["latents"].copy_(snap["latents"])
             st["pano"].copy_(snap["pano"])

@@ -90,8 +90,23 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="panorama branch on the main stream (serialised)")
     ap.add_argument("--pano-only", action="store_true", help="time the panorama branch alone (unet=None), batch = "
                     "2 / batch_shards, as a CUDA graph of MultiViewBaseModel.forward")
+    ap.add_argument("--profile-one-step", action="store_true", help="under `ncu --profile-from-start off`: one EAGER "
+                    "step of the first layout between cudaProfilerStart/Stop (launch list of one emulated rank)")
     args = ap.parse_args()
     dev, dt = torch.device("cuda:0"), torch.bfloat16
+    if args.profile_one_step:
+        lay = args.layouts.split(",")[0]
+        model, sampler = build(args.workload, dev, dt, tuple(int(v) for v in lay.split("x")), graph=False,
+                               overlap=not args.no_overlap)
+        for i in range(4):
+            sampler.step(i)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        sampler.step(4)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps(dict(layout=lay, profiled_step_launches=sampler.launches_per_step)))
+        return
     for lay in args.layouts.split(","):
         layout = tuple(int(v) for v in lay.split("x"))
         if args.pano_only:

@@ -207,6 +207,28 @@ def test_eppa_tables_vs_reference_goldens(cuda_device):
         torch.testing.assert_close(b2.cpu(), ref2, rtol=1e-5, atol=2e-6)
 
 
+def test_eppa_tables_config4_level_size_vs_reference_golden(cuda_device):
+    """pf_eppa_tables at config 4's real first EPPA level (32x32 views / 64x128 pano, icosahedron rings) against the
+    reference-run golden: a strided subset of the query rows element-wise, the key-sum of EVERY row."""
+    from pathlib import Path
+    import numpy as np
+    from oracle.make_golden import C4GEO_LEVEL, _cams_ico
+    from panfusion_b200 import geometry as pg, ops
+    gold = np.load(Path(__file__).parent / "golden" / "eppa_geometry_c4_level.npz")
+    ph, pw, eh, ew = C4GEO_LEVEL
+    cams = _cams_ico()
+    V, P, E = len(cams["FoV"]), ph * pw, eh * ew
+    ce, _ = pg.camera_records("e2p", cams["FoV"], cams["theta"], cams["phi"], V, ph, pw, cuda_device)
+    cp, _ = pg.camera_records("p2e", cams["FoV"], cams["theta"], cams["phi"], V, ph, pw, cuda_device)
+    b1, b2 = ops.eppa_tables(ce, cp, V, ph, pw, eh, ew)          # [1, E, V*P], [1, V*P, E]
+    pm = b1.reshape(eh, ew, V, ph, pw).permute(2, 0, 1, 3, 4)     # -> pers_masks [V, eh, ew, ph, pw] (modules.py:46)
+    em = b2.reshape(V, ph, pw, eh, ew)                            # -> equi_masks [V, ph, pw, eh, ew] (modules.py:53)
+    torch.testing.assert_close(pm[:, ::7, ::9].cpu(), torch.from_numpy(gold["pers_rows"]), rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(em[:, ::5, ::5].cpu(), torch.from_numpy(gold["equi_rows"]), rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(pm.double().sum((-1, -2)).cpu(), torch.from_numpy(gold["pers_rowsum"]), rtol=0, atol=2e-3)
+    torch.testing.assert_close(em.double().sum((-1, -2)).cpu(), torch.from_numpy(gold["equi_rowsum"]), rtol=0, atol=2e-3)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.uint8])
 def test_pad_pano_bit_exact(cuda_device, dtype):
     """pad_pano / unpad_pano (utils/pano.py:74-105): 4-D and 5-D, every dtype width, against the oracle restatement

@@ -5,11 +5,13 @@
 Tolerances. The north star asks rtol 1e-3 / atol 1e-4 "fp16"; that bar is met per kernel (tests/test_gpu_gemm.py,
 test_gpu_fmha.py, test_gpu_kernels.py, test_gpu_resample.py compare each kernel with an fp32 reference on
 16-bit-rounded inputs). End to end the activations are ROUNDED TO 16 BIT between ~400 kernels, which the fp32
-reference never does, so the whole-model comparison is bounded by accumulated storage rounding instead:
-fp16 (11-bit significand)  : max |err| <= 1.5e-2 * max|ref|, mean |err| <= 2e-3 * max|ref|
-bf16 ( 8-bit significand)  : max |err| <= 8e-2  * max|ref|, mean |err| <= 1.2e-2 * max|ref|
-(measured values are printed; see DESIGN.md "Parity").
+reference never does, so the whole-model comparison is bounded by accumulated storage rounding instead. The gates
+are set at about TWICE what was measured on B200 (DESIGN.md "Parity" lists the measured values), relative to
+max|ref|, so a 2x regression of the end-to-end agreement fails:
+fp16 (11-bit significand)  : max |err| <= 4e-3,   mean |err| <= 5e-4    (measured 1.3e-3 .. 1.8e-3 / 2.2e-4)
+bf16 ( 8-bit significand)  : max |err| <= 2.5e-2, mean |err| <= 4e-3    (measured 1.0e-2 .. 1.2e-2 / 1.8e-3)
 """
+import functools
 from pathlib import Path
 
 import numpy as np
@@ -20,6 +22,16 @@ pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).parent / "golden"
 
 
+LIMITS = {torch.float16: (4e-3, 5e-4), torch.bfloat16: (2.5e-2, 4e-3)}
+
+
+@functools.lru_cache(maxsize=2)
+def _oracle_model(config_name: str):
+    """The seeded oracle model (weights only are used on the GPU side); SD-2 size takes ~1 min of host RNG: shared."""
+    from oracle import mvgen as om, synth, unet as ou
+    return synth.build_model(om.MultiViewBaseModel, getattr(ou, config_name), seed=0)
+
+
 def _err(got, ref):
     scale = ref.abs().max().item()
     d = (got - ref).abs()
@@ -28,7 +40,7 @@ def _err(got, ref):
 
 def _check(name, got, ref, dtype):
     mx, mean = _err(got.float().cpu(), ref)
-    lim = (1.5e-2, 2e-3) if dtype == torch.float16 else (8e-2, 1.2e-2)
+    lim = LIMITS[dtype]
     print(f"[parity] {name} {dtype}: max {mx:.3e} mean {mean:.3e} (of max|ref|) limits {lim}")
     assert mx <= lim[0] and mean <= lim[1], (name, mx, mean)
 
@@ -60,14 +72,20 @@ def test_warpattn_vs_reference_golden(cuda_device, dtype):
     _check("WarpAttn equi update", ge.float().cpu() - ex, torch.from_numpy(gold["equi_out"]) - ex, dtype)
 
 
-def _run_mvgen(cuda_device, config, pano_hw, pers_hw, dtype):
-    from oracle import mvgen as om, synth
+def _build_mine(cuda_device, config, dtype):
+    from oracle import unet as ou
     from panfusion_b200.mvgen import MultiViewBaseModel
-    orc = synth.build_model(om.MultiViewBaseModel, config, seed=0)
-    inp = synth.step_inputs(2, pano_hw, pers_hw, config["cross_attention_dim"], seed=0)
+    orc = _oracle_model("SD2_CONFIG" if config is ou.SD2_CONFIG else "TINY_CONFIG")
     mine = MultiViewBaseModel(orc.unet, orc.pano_unet, compute_dtype=dtype)
     mine.load_state_dict(orc.state_dict())
     mine.prepare(cuda_device, dtype)
+    return orc, mine
+
+
+def _run_mvgen(cuda_device, config, pano_hw, pers_hw, dtype):
+    from oracle import synth
+    orc, mine = _build_mine(cuda_device, config, dtype)
+    inp = synth.step_inputs(2, pano_hw, pers_hw, config["cross_attention_dim"], seed=0)
     cu = {k: (v.to(cuda_device) if torch.is_tensor(v) else {kk: vv.to(cuda_device) for kk, vv in v.items()})
           for k, v in inp.items()}
     s, p = mine(**cu)
@@ -97,6 +115,34 @@ def test_mvgen_c1_vs_reference_golden(cuda_device, dtype):
     gold = np.load(GOLD / "mvgen_c1.npz")
     _check("MultiViewBaseModel C1 sample", s, torch.from_numpy(gold["sample"]), dtype)
     _check("MultiViewBaseModel C1 pano", p, torch.from_numpy(gold["pano_sample"]), dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_mvgen_c2_vs_reference_golden(cuda_device, dtype):
+    """BASELINE configs[1] — the BENCHMARKED configuration (SD-2 widths, 8 horizon views 64x64 + pano 64x128, the CFG
+    pair b = 2 with prompts [null; text]): golden = the reference's own MultiViewBaseModel.forward (MVGenModel.py:38-297)
+    executed on CPU in the build container (oracle/make_golden.py --only c2). Then the SAME step through the sharded
+    code path: every rank of the 2x1 (N = 2) and 2x4 (N = 8) layouts runs on this GPU in turn (tests/_rank_replay.py) and
+    the assembled result must equal the unsharded one."""
+    from oracle import synth, unet as ou
+    from _rank_replay import run_all_ranks, run_unsharded_recording
+    cfg = ou.SD2_CONFIG
+    _, mine = _build_mine(cuda_device, cfg, dtype)
+    inp = _to_dev(synth.step_inputs_cfg(8, (64, 128), (64, 64), cfg["cross_attention_dim"], seed=0), cuda_device)
+    (s, p), rec = run_unsharded_recording(mine, inp)
+    torch.cuda.synchronize()
+    gold = np.load(GOLD / "mvgen_c2.npz")
+    _check("MultiViewBaseModel C2 sample", s, torch.from_numpy(gold["sample"]), dtype)
+    _check("MultiViewBaseModel C2 pano", p, torch.from_numpy(gold["pano_sample"]), dtype)
+    # CFG halves see different prompts: they must differ (a broken batch index would make them equal)
+    assert (s[0] - s[1]).abs().max().item() > 1e-3
+    assert len(rec) == 7
+    for layout in ((2, 1), (2, 4)):
+        ss, sp, worst = run_all_ranks(mine, inp, *layout, rec)
+        ds, dp = (ss - s).abs().max().item(), (sp - p).abs().max().item()
+        print(f"[parity] C2 {dtype} layout {layout[0]}x{layout[1]}: |sharded - unsharded| sample {ds:.3e} pano {dp:.3e}, "
+              f"local K|V vs unsharded {worst:.3e}")
+        assert ds == 0.0 and dp == 0.0 and worst == 0.0
 
 
 def _build_cn_pair(cuda_device, config, dtype, pers):

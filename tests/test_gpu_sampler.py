@@ -103,3 +103,56 @@ def test_layout_conditioned_steps_vs_oracle_and_graph_replay(cuda_device):
         err = (got - ref).abs().max().item() / ref.abs().max().item()
         print(f"[parity] {n}-step layout-conditioned sampler {name}: max err {err:.3e} of max|ref|")
         assert err < 3e-2
+
+
+def test_sampler_reuses_buffers_and_graphs_across_images(cuda_device):
+    """A second denoise() of the same shapes on the same sampler (new noise, new prompt) must replay the graphs captured
+    for the first image — no new captures — and give exactly what a fresh sampler gives: the inputs are copied into the
+    static buffers and the text K/V are re-projected in place (the captured step does not contain that projection)."""
+    from oracle import mvgen as om, sampler as osamp, synth, unet as ou
+    from panfusion_b200.mvgen import MultiViewBaseModel
+    from panfusion_b200.sampler import PanFusionSampler
+    cfg, dtype = ou.TINY_CONFIG, torch.float16
+    orc = synth.build_model(om.MultiViewBaseModel, cfg, seed=0)
+    mine = MultiViewBaseModel(orc.unet, orc.pano_unet, compute_dtype=dtype)
+    mine.load_state_dict(orc.state_dict())
+    mine.prepare(cuda_device, dtype)
+    m, n = 4, 6
+    cams = osamp.horizon_cameras(m)
+
+    def image(seed):
+        g = torch.Generator().manual_seed(seed)
+        pano = torch.randn(1, 1, 4, 16, 32, generator=g)
+        lat = osamp.init_noise(pano, 16, 16, cams)
+        text = torch.randn(1, 1, 77, cfg["cross_attention_dim"], generator=g)
+        null = torch.randn(1, 1, 77, cfg["cross_attention_dim"], generator=g)
+        to = lambda t: t.to(cuda_device)
+        return to(lat), to(pano), to(torch.cat([null.repeat(1, m, 1, 1), text.repeat(1, m, 1, 1)])), to(torch.cat([null, text]))
+
+    s = PanFusionSampler(mine, use_cuda_graph=True)
+    a1 = s.denoise(*image(1), cams, num_steps=n)
+    graphs_after_first = dict(s._graphs)
+    assert len(graphs_after_first) == 4  # one per rotation phase
+    b1 = s.denoise(*image(2), cams, num_steps=n)
+    assert s._graphs.keys() == graphs_after_first.keys() and all(s._graphs[k] is v for k, v in graphs_after_first.items())
+    fresh = PanFusionSampler(mine, use_cuda_graph=True)
+    b2 = fresh.denoise(*image(2), cams, num_steps=n)
+    assert torch.equal(b1[0], b2[0]) and torch.equal(b1[1], b2[1])
+    assert not torch.equal(a1[1], b1[1])
+    # and the first image again on the reused sampler
+    a2 = s.denoise(*image(1), cams, num_steps=n)
+    assert torch.equal(a1[0], a2[0]) and torch.equal(a1[1], a2[1])
+
+
+def test_camera_table_cache_is_bounded(cuda_device):
+    """CameraTables is an LRU over camera sets: random rigs must not grow device memory without limit, and an evicted
+    set is rebuilt on demand with identical contents."""
+    from panfusion_b200.eppa import CameraTables
+    tabs = CameraTables(max_camera_sets=2)
+    rigs = [tuple((tuple([90.0] * 2), tuple([float(t), float(t) + 180.0]), tuple([0.0, 0.0]))) for t in (0, 30, 60)]
+    first = [tabs.bias(r, 1, 8, 8, 8, 16, cuda_device)[0].clone() for r in rigs]
+    assert len(tabs._lru) == 2 and rigs[0] not in tabs._lru
+    assert all(tabs._key_of(k) in tabs._lru for cache in (tabs._bias, tabs._rec) for k in cache)
+    again = tabs.bias(rigs[0], 1, 8, 8, 8, 16, cuda_device)[0]
+    assert torch.equal(again, first[0]) and rigs[1] not in tabs._lru
+    assert len(tabs.tensors_of(rigs[0])) >= 4

@@ -57,6 +57,19 @@ def test_eppa_geometry_config4_matches_reference_golden():
     np.testing.assert_array_equal(ec.numpy(), gold["equi_coords"])
 
 
+def test_eppa_geometry_config4_level_size_matches_reference_golden():
+    """get_masks at config 4's REAL first EPPA level (32x32 views / 64x128 pano, one camera per icosahedron ring):
+    the fixture holds a strided subset of the query rows plus the key-sum of EVERY row of the reference output."""
+    from oracle.make_golden import C4GEO_LEVEL, _cams_ico, c4geo_subsample
+    gold = np.load(GOLD / "eppa_geometry_c4_level.npz")
+    pm, em = oe.get_masks(*C4GEO_LEVEL, _cams_ico())
+    mine = c4geo_subsample(pm, em)
+    for k in ("pers_rows", "equi_rows"):
+        np.testing.assert_allclose(mine[k], gold[k], rtol=0, atol=1e-6)
+    for k in ("pers_rowsum", "equi_rowsum"):
+        np.testing.assert_allclose(mine[k], gold[k], rtol=0, atol=1e-3)
+
+
 def test_mask_edge_cases():
     """Camera looking at the pole / FoV so narrow that many queries have no correspondence: rows stay -1."""
     c = dict(FoV=torch.tensor([30.0]), theta=torch.tensor([10.0]), phi=torch.tensor([85.0]))
