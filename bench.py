@@ -427,10 +427,10 @@ def image_latency(model, inp, wl, dev, n_steps=50):
         t0 = time.perf_counter()
         images, pano = sampler.inference(inp["cams"], prompt, pano_prompt, dec, wl["pano_hw"], wl["pers_hw"], device=dev,
                                          generator=g, num_steps=n_steps)
-        h_img, h_pano = images.cpu(), pano.cpu()
+        h_img, h_pano = images, pano   # uint8 numpy on the host, like the reference's tensor_to_image
         out[tag] = round(time.perf_counter() - t0, 4)
     out["what"] = (f"sampler.inference: init_noise + {n_steps} denoise steps + rotate back + VAE decode of {wl['m']} views "
-                   f"and the padded panorama + tensor_to_image + device->host of the uint8 images")
+                   f"and the padded panorama + tensor_to_image (uint8 images returned on the host)")
     out["image_shapes"] = [list(h_img.shape), list(h_pano.shape)]
     return out
 

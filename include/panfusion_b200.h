@@ -103,9 +103,25 @@ typedef struct pf_gemm_args {
    * a second kernel reduces them in a fixed order and applies the epilogue. 0 / 1 = off. */
   int32_t k_splits;
   float* splitk_ws;
+  /* LayerNorm fused around the GEMM (diffusers BasicTransformerBlock norm1/2/3 -> to_q|k|v / to_q / GEGLU proj, and
+   * models/modules/transformer.py:159-160 norm2 -> ff): instead of a LayerNorm kernel between two linears,
+   *   PRODUCER (row_stats_out != NULL): besides `out`, writes per output row the partial (sum, sum of squares) of the
+   *     final fp32 values of every column slot: row_stats_out[m][slot][2], slots = pf_gemm_row_stats_slots(args).
+   *   CONSUMER (ln_stats != NULL): A is the UN-normalised tensor, B holds gamma-scaled weights W'[n,k] = gamma[k] W[n,k],
+   *     ln_colsum[n] = sum_k W'[n,k] (of the 16-bit rounded W'), bias[n] = sum_k beta[k] W[n,k] + b[n]; the epilogue applies
+   *     acc <- rstd[m] * (acc - mean[m] * ln_colsum[n]) with mean / rstd from ln_stats[m][ln_slots][2] over K = Kc*num_taps
+   *     elements, biased variance, eps = ln_eps — algebraically LayerNorm(A) W^T + b with the normalised tensor never
+   *     stored. Supported with the plain row map and 16-bit output, or with the GEGLU epilogue. */
+  float* row_stats_out;
+  const float* ln_stats;
+  int32_t ln_slots;
+  const float* ln_colsum;
+  float ln_eps;
 } pf_gemm_args;
 
 int pf_gemm_taps(const pf_gemm_args* args, void* stream);
+/* number of column slots a producer with these args writes per row of row_stats_out (depends on the tile width) */
+int pf_gemm_row_stats_slots(const pf_gemm_args* args);
 /* suggested k_splits for this problem (1 = do not split); only M, N, Kc, num_taps, act, map_mode, dtypes are read */
 int pf_gemm_splitk_plan(const pf_gemm_args* args);
 /* block_n the auto-tuner would pick for this N (used by the host-side weight packer for GEGLU) */
@@ -171,6 +187,21 @@ int pf_groupnorm_stats(const void* x, int dtype, int N, int H, int W, int C, int
 int pf_conv_prep(const void* x, void* out, int dtype, int N, int H, int W, int C, int ld, const float* mean_rstd,
                  const float* gamma, const float* beta, int groups, int act, int circ, int up, int phases, int halo,
                  void* stream);
+
+/* pf_groupnorm_stats + pf_conv_prep in ONE launch (same semantics, same reference call sites), optionally over the channel
+ * concatenation of two tensors (torch.cat([hidden, skip], dim=1) at MVGenModel.py:223,231,246,254):
+ *   x = cat(x1[N*H*W, C1], x2[N*H*W, C2]) (x2 may be NULL); if cat_out != NULL the raw concatenation [N*H*W, C1+C2] is also
+ *   written (the ResnetBlock2D shortcut convolution reads it);
+ *   statistics over the image circularly extended by circ_stats columns (duplicated columns count twice), applied with
+ *   gamma / beta (+ SiLU) while building the conv_prep layout (circ, up, phases, halo as in pf_conv_prep).
+ * The kernel holds a per-image barrier between the statistics and the apply phase (the source is re-read from L2), so its
+ * grid is capped at 148 CTAs of <= 512 threads — two such launches (the two UNet branches' streams) are always co-resident.
+ * ws: pf_gn_prep_ws_floats(N, groups) floats of scratch; sync: 3*N ints that are ZERO on entry (restored to zero by the
+ * kernel; concurrent launches need distinct slots). N <= 148. */
+int pf_gn_prep_ws_floats(int N, int groups);
+int pf_gn_prep(const void* x1, int ld1, int C1, const void* x2, int ld2, int C2, void* cat_out, void* out, int dtype,
+               int N, int H, int W, int groups, float eps, const float* gamma, const float* beta, int act,
+               int circ_stats, int circ, int up, int phases, int halo, float* ws, int* sync, void* stream);
 
 /* out[t, :] = LayerNorm(x[t, :] + pe[t % pe_rows, :]) * gamma + beta (pe fp32, may be NULL);
  * models/modules/transformer.py:157-160 (EPPA norm1 on x + query_pe / context, norm2) and the diffusers

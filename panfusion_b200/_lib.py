@@ -36,6 +36,8 @@ class GemmArgs(C.Structure):
         ("map_mode", C.c_int32), ("Hm", C.c_int32), ("Wm", C.c_int32), ("i0", C.c_int32), ("j0", C.c_int32),
         ("Hout", C.c_int32), ("Wout", C.c_int32),
         ("k_splits", C.c_int32), ("splitk_ws", C.c_void_p),
+        ("row_stats_out", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_slots", C.c_int32), ("ln_colsum", C.c_void_p),
+        ("ln_eps", C.c_float),
     ]
 
 
@@ -74,9 +76,9 @@ def lib() -> C.CDLL:
 EXPORTS = [
     "pf_last_error", "pf_version", "pf_check_device",
     "pf_e2p", "pf_p2e",
-    "pf_gemm_taps", "pf_gemm_pick_block_n", "pf_gemm_splitk_plan",
+    "pf_gemm_taps", "pf_gemm_pick_block_n", "pf_gemm_splitk_plan", "pf_gemm_row_stats_slots",
     "pf_fmha_fwd", "pf_bias_tile_flags",
-    "pf_groupnorm_ws_floats", "pf_groupnorm_stats", "pf_conv_prep", "pf_layernorm",
+    "pf_groupnorm_ws_floats", "pf_groupnorm_stats", "pf_conv_prep", "pf_gn_prep_ws_floats", "pf_gn_prep", "pf_layernorm",
     "pf_conv_in", "pf_conv_out", "pf_copy2d", "pf_pad_pano", "pf_softmax_rows", "pf_tensor_to_image", "pf_timestep_embed", "pf_cfg_ddim_step", "pf_cfg_ddim_step_dev",
     "pf_eppa_tables", "pf_eppa_pe",
 ]

@@ -24,7 +24,30 @@ struct GemmKernelParams {
   int map_mode, Hm, Wm, i0, j0, Hout, Wout;
   int k_splits;     // > 1: blockIdx.y = split index, raw fp32 partials go to ws
   float* ws;        // [k_splits][M][N]
+  // fused LayerNorm (see pf_gemm_args): producer side / consumer side
+  float* row_stats;        // [M][stat_slots][2] or null
+  int stat_slots;          // 2 * n_tiles
+  const float* ln_stats;   // [M][ln_slots][2] or null
+  int ln_slots;
+  const float* ln_colsum;  // [N]
+  float ln_inv_k, ln_eps;
 };
+
+// mean / rstd of one row from the producer's partial sums, as the two epilogue coefficients of the LayerNorm fold:
+// acc <- acc * a + colsum[n] * b with a = rstd, b = -mean * rstd
+__device__ __forceinline__ void ln_row_coeffs(const GemmKernelParams& p, long long m, float& a, float& b) {
+  const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + m * p.ln_slots;
+  float s = 0.f, q = 0.f;
+  for (int i = 0; i < p.ln_slots; ++i) {
+    const float2 v = __ldg(st + i);
+    s += v.x;
+    q += v.y;
+  }
+  const float mean = s * p.ln_inv_k;
+  const float var = fmaxf(q * p.ln_inv_k - mean * mean, 0.f);
+  a = rsqrtf(var + p.ln_eps);
+  b = -mean * a;
+}
 
 __host__ __device__ constexpr int gemm_stage_bytes(int block_n) {
   return GEMM_BLOCK_M * GEMM_BLOCK_K * 2 + block_n * GEMM_BLOCK_K * 2;

@@ -20,7 +20,7 @@ constexpr int PG_EPI_THREADS = 256;
 __host__ __device__ constexpr int pg_acc_stride(int block_n) { return block_n <= 64 ? 64 : block_n <= 128 ? 128 : 256; }
 __host__ __device__ constexpr int pg_smem_bytes(int block_n, int stages, bool epi_tma) {
   return stages * gemm_stage_bytes(block_n) + (epi_tma ? 2 * GEMM_BLOCK_M * block_n * 2 : 0) + 256 /*barriers*/ +
-         2 * block_n * 4 /*bias rows*/;
+         4 * block_n * 4 /*bias rows + LayerNorm column sums*/;
 }
 
 template <int BLOCK_N, int STAGES, bool BF16, bool EPI_TMA>
@@ -49,6 +49,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* stg_empty = res_full + 2;         // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(stg_empty + 2);
   float* s_bias = reinterpret_cast<float*>(staging + 2 * STAGING_BYTES + 256);  // [2][BLOCK_N]
+  float* s_cs = s_bias + 2 * BLOCK_N;                                            // [2][BLOCK_N] LayerNorm column sums
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -148,6 +149,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n0 = (blockIdx.x % n_tiles) * BLOCK_N;
       if (et < BLOCK_N) s_bias[et] = __ldg(p.bias + n0 + et);
     }
+    if (p.ln_stats && blockIdx.x < num_tiles) {
+      const int n0 = (blockIdx.x % n_tiles) * BLOCK_N;
+      if (et < BLOCK_N) s_cs[et] = __ldg(p.ln_colsum + n0 + et);
+    }
     named_bar_sync(1, PG_EPI_THREADS);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -160,11 +165,17 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int next_tile = tile + gridDim.x;
       if (p.bias && next_tile < num_tiles && et < BLOCK_N)
         bias_next = __ldg(p.bias + (next_tile % n_tiles) * BLOCK_N + et);
+      const float* cs_s = s_cs + (it & 1) * BLOCK_N;
+      float cs_next = 0.f;
+      if (p.ln_stats && next_tile < num_tiles && et < BLOCK_N)
+        cs_next = __ldg(p.ln_colsum + (next_tile % n_tiles) * BLOCK_N + et);
 
       const int m = m0 + row;
       bool valid = m < p.M;
       long long orow = m;
       int group = 0;
+      float ln_a = 1.f, ln_b = 0.f;
+      if (p.ln_stats && valid) ln_row_coeffs(p, m, ln_a, ln_b);
       if (p.map_mode == 1) {
         const int hw = p.Hm * p.Wm;
         const int img = m / hw;
@@ -193,6 +204,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         named_bar_sync(2, PG_EPI_THREADS);
         if (p.residual) mbar_wait(&res_full[buf], (it >> 1) & 1);
+        float st_s = 0.f, st_q = 0.f;
 #pragma unroll 1
         for (int ci = half; ci < NCH; ci += 2) {
           const int c = ci * 16;
@@ -202,6 +214,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float o[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[e]);
+          if (p.ln_stats) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = fmaf(o[e], ln_a, cs_s[c + e] * ln_b);
+          }
           if (p.bias) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) o[e] += bias_s[c + e];
@@ -233,14 +249,24 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             f = unpack2<BF16>(r1.z); o[12] += f.x; o[13] += f.y;
             f = unpack2<BF16>(r1.w); o[14] += f.x; o[15] += f.y;
           }
+          if (p.row_stats) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              st_s += o[e];
+              st_q = fmaf(o[e], o[e], st_q);
+            }
+          }
           *s0 = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]), pack2<BF16>(o[4], o[5]),
                            pack2<BF16>(o[6], o[7]));
           *s1 = make_uint4(pack2<BF16>(o[8], o[9]), pack2<BF16>(o[10], o[11]), pack2<BF16>(o[12], o[13]),
                            pack2<BF16>(o[14], o[15]));
         }
+        if (p.row_stats && valid)
+          reinterpret_cast<float2*>(p.row_stats)[(long long)m * p.stat_slots + n_tile * 2 + half] = make_float2(st_s, st_q);
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);  // accumulator stage free for the MMAs of tile it+2
         if (p.bias && et < BLOCK_N) s_bias[((it + 1) & 1) * BLOCK_N + et] = bias_next;
+        if (p.ln_stats && et < BLOCK_N) s_cs[((it + 1) & 1) * BLOCK_N + et] = cs_next;
         fence_proxy_async_smem();
         named_bar_sync(1, PG_EPI_THREADS);
         if (et == 0) {
@@ -287,6 +313,13 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 } else {
 #pragma unroll
                   for (int e = 0; e < 16; ++e) ba[e] = bg[e] = 0.f;
+                }
+                if (p.ln_stats) {
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) {
+                    va[e] = __float_as_uint(fmaf(__uint_as_float(va[e]), ln_a, cs_s[c + e] * ln_b));
+                    vg[e] = __float_as_uint(fmaf(__uint_as_float(vg[e]), ln_a, cs_s[HALF_N + c + e] * ln_b));
+                  }
                 }
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
@@ -391,6 +424,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
         if (p.bias && et < BLOCK_N) s_bias[((it + 1) & 1) * BLOCK_N + et] = bias_next;
+        if (p.ln_stats && et < BLOCK_N) s_cs[((it + 1) & 1) * BLOCK_N + et] = cs_next;
         named_bar_sync(1, PG_EPI_THREADS);  // publishes the next bias row; keeps the two bias buffers in step
       }
     }

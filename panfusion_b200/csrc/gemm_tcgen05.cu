@@ -19,7 +19,7 @@ __host__ __device__ constexpr int gemm_tmem_cols(int block_n) {
   return block_n <= 32 ? 32 : block_n <= 64 ? 64 : block_n <= 128 ? 128 : block_n <= 256 ? 256 : 512;
 }
 __host__ __device__ constexpr int gemm_smem_bytes(int block_n, int stages) {
-  return stages * gemm_stage_bytes(block_n) + 128 /*barriers*/ + block_n * 4 /*bias row*/;
+  return stages * gemm_stage_bytes(block_n) + 128 /*barriers*/ + 2 * block_n * 4 /*bias row + LayerNorm column sums*/;
 }
 
 // EPI_TMA: plain row map + 16-bit output. The output tile is staged in shared memory as BLOCK_N/32 sub-tiles of
@@ -55,6 +55,7 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* res_full_bar = tmem_full_bar + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_full_bar + 1);
   float* s_bias = reinterpret_cast<float*>(staging + STAGING_BYTES + 128);  // [BLOCK_N]
+  float* s_cs = s_bias + BLOCK_N;                                            // [BLOCK_N] LayerNorm column sums
 
   pdl_launch_dependents();  // the next kernel of the stream may start its prologue while this one runs
   const int warp = threadIdx.x >> 5;
@@ -192,6 +193,11 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.bias) {
       for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) s_bias[i] = __ldg(p.bias + n0 + i);
     }
+    float ln_a = 1.f, ln_b = 0.f;
+    if (p.ln_stats) {
+      for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) s_cs[i] = __ldg(p.ln_colsum + n0 + i);
+      if (m < p.M) ln_row_coeffs(p, m, ln_a, ln_b);
+    }
     named_bar_sync(1, 128);
 
     if (p.k_splits > 1) {
@@ -218,6 +224,7 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       if (p.residual) mbar_wait(res_full_bar, 0);
       const uint32_t sw = uint32_t((row >> 1) & 3);  // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
+      float st_s = 0.f, st_q = 0.f;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 16) {
         uint32_t v[16];
@@ -226,6 +233,10 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float o[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[e]);
+        if (p.ln_stats) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] = fmaf(o[e], ln_a, s_cs[c + e] * ln_b);
+        }
         if (p.bias) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) o[e] += s_bias[c + e];
@@ -258,10 +269,22 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           f = unpack2<BF16>(r1.z); o[12] += f.x; o[13] += f.y;
           f = unpack2<BF16>(r1.w); o[14] += f.x; o[15] += f.y;
         }
+        if (p.row_stats) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            st_s += o[e];
+            st_q = fmaf(o[e], o[e], st_q);
+          }
+        }
         *s0 = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]), pack2<BF16>(o[4], o[5]),
                          pack2<BF16>(o[6], o[7]));
         *s1 = make_uint4(pack2<BF16>(o[8], o[9]), pack2<BF16>(o[10], o[11]), pack2<BF16>(o[12], o[13]),
                          pack2<BF16>(o[14], o[15]));
+      }
+      if (p.row_stats && m < p.M) {  // one thread covers the whole tile row: the second slot of the pair stays zero
+        float2* st = reinterpret_cast<float2*>(p.row_stats) + (long long)m * p.stat_slots + n_tile * 2;
+        st[0] = make_float2(st_s, st_q);
+        st[1] = make_float2(0.f, 0.f);
       }
       fence_proxy_async_smem();           // generic-proxy writes -> visible to the TMA store
       named_bar_sync(1, 128);             // the four epilogue warps only
@@ -294,6 +317,13 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             } else {
 #pragma unroll
               for (int e = 0; e < 16; ++e) ba[e] = bg[e] = 0.f;
+            }
+            if (p.ln_stats) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                va[e] = __float_as_uint(fmaf(__uint_as_float(va[e]), ln_a, s_cs[c + e] * ln_b));
+                vg[e] = __float_as_uint(fmaf(__uint_as_float(vg[e]), ln_a, s_cs[HALF + c + e] * ln_b));
+              }
             }
 #pragma unroll
             for (int e = 0; e < 16; ++e)
@@ -579,7 +609,7 @@ static int launch_gemm_pair(const pf_gemm_args* a, const GemmKernelParams& kp, c
     uint32_t box[2] = {GEMM_BLOCK_K, (uint32_t)BLOCK_N / 2};  // each CTA of the pair stages half of the weight tile
     if ((rc = make_tmap(&tmB, a->dtype, 2, a->B, dims, str, box, 128))) return rc;
   }
-  constexpr int SMEM = STAGES * (GEMM_BLOCK_M * GEMM_BLOCK_K * 2 + (BLOCK_N / 2) * GEMM_BLOCK_K * 2) + 128 + BLOCK_N * 4;
+  constexpr int SMEM = STAGES * (GEMM_BLOCK_M * GEMM_BLOCK_K * 2 + (BLOCK_N / 2) * GEMM_BLOCK_K * 2) + 128 + 2 * BLOCK_N * 4;
   const int m_pairs = (a->M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * m_pairs * (a->N / BLOCK_N));
@@ -617,6 +647,22 @@ static int launch_gemm_pair(const pf_gemm_args* a, const GemmKernelParams& kp, c
 }
 
 }  // namespace pf
+
+namespace pf {
+// tile width pf_gemm_taps runs with: the caller's / tuner's request, else the heuristic; the staged (TMA-store) epilogue
+// that carries the fused-LayerNorm statistics has no 256-wide variant
+static int resolve_block_n(const pf_gemm_args* a) {
+  int bn = (a->block_n & 0xffff) ? (a->block_n & 0xffff) : pf_gemm_pick_block_n(a->N, a->act);
+  if ((a->row_stats_out || a->ln_stats) && a->act != PF_ACT_GEGLU && bn == 256) bn = 128;
+  return bn;
+}
+}  // namespace pf
+
+extern "C" int pf_gemm_row_stats_slots(const pf_gemm_args* a) {
+  if (!a || a->N <= 0) return 0;
+  const int bn = pf::resolve_block_n(a);
+  return bn > 0 && a->N % bn == 0 ? 2 * (a->N / bn) : 0;
+}
 
 extern "C" int pf_gemm_pick_block_n(int N, int act) {
   // GEGLU tiles are epilogue-bound (one erf-GELU per output, K as short as 5 slabs): the 256-wide tile gives each
@@ -663,7 +709,7 @@ extern "C" int pf_gemm_taps(const pf_gemm_args* a, void* stream) {
   // block_n: low 16 bits = tile width (0 = auto); bits 16.. = schedule override (0 auto, 1 one-tile-per-CTA,
   // 2 persistent, 3 CTA pair) — written by scripts/tune_gemm.py into gemm_tuning.json, never needed by callers
   const int sched_req = a->block_n >> 16;
-  int bn = (a->block_n & 0xffff) ? (a->block_n & 0xffff) : pf_gemm_pick_block_n(a->N, a->act);
+  int bn = pf::resolve_block_n(a);
   PF_CHECK_ARG(bn == 64 || bn == 128 || bn == 160 || bn == 256, "pf_gemm_taps: unsupported block_n %d (N=%d)", bn, a->N);
   PF_CHECK_ARG(a->N % bn == 0, "pf_gemm_taps: N=%d not a multiple of block_n=%d", a->N, bn);
   const int n_out = a->act == PF_ACT_GEGLU ? a->N / 2 : a->N;
@@ -705,8 +751,25 @@ extern "C" int pf_gemm_taps(const pf_gemm_args* a, void* stream) {
   kp.Wout = a->Wout;
   kp.k_splits = a->k_splits > 1 ? a->k_splits : 1;
   kp.ws = a->splitk_ws;
+  kp.row_stats = a->row_stats_out;
+  kp.stat_slots = 2 * (a->N / bn);
+  kp.ln_stats = a->ln_stats;
+  kp.ln_slots = a->ln_slots;
+  kp.ln_colsum = a->ln_colsum;
+  kp.ln_inv_k = 1.0f / float((long long)a->Kc * a->num_taps);
+  kp.ln_eps = a->ln_eps;
   PF_CHECK_ARG(kp.k_splits == 1 || (a->splitk_ws && a->act != PF_ACT_GEGLU && kp.k_splits <= kp.num_kb),
                "pf_gemm_taps: split-K needs a workspace, no GEGLU and k_splits <= K-slabs");
+  const bool fused_ln = a->row_stats_out || a->ln_stats;
+  if (fused_ln) {
+    PF_CHECK_ARG(kp.k_splits == 1, "pf_gemm_taps: fused LayerNorm does not combine with split-K");
+    PF_CHECK_ARG(!a->ln_stats || (a->ln_colsum && a->ln_slots > 0 && a->ln_eps > 0.f),
+                 "pf_gemm_taps: ln_stats needs ln_colsum, ln_slots and ln_eps");
+    const bool plain16 = a->map_mode == 0 && a->out_dtype == a->dtype && (!a->residual || a->res_dtype == a->dtype) &&
+                         (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0;
+    PF_CHECK_ARG(a->act == PF_ACT_GEGLU ? !a->row_stats_out : plain16,
+                 "pf_gemm_taps: fused LayerNorm needs the plain row map with 16-bit output (consumer: or GEGLU)");
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (kp.k_splits > 1) {
     int rc;

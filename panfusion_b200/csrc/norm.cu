@@ -208,6 +208,253 @@ __global__ void __launch_bounds__(256) conv_prep_kernel(const PrepParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// gn_prep: GroupNorm statistics + apply (+SiLU) + conv_prep layout in ONE launch (pf_gn_prep).
+//
+// grid = (chunks, N) with chunks * N <= GNP_MAX_CTAS, so that every CTA of the launch (and of one more such launch on
+// the other branch's stream) is co-resident: the kernel contains a per-image barrier. Phase 1: each CTA sums its band
+// of source pixels per channel (two sources = the skip concatenation torch.cat([hidden, skip], 1), optionally also
+// written out raw), publishes per-group partials, and the LAST CTA of the image to arrive reduces them in a fixed
+// order (deterministic) into mean / rstd and releases the image's flag. Phase 2: after acquiring the flag each CTA
+// produces its share of the image's output positions — the source pixels are re-read from L2, not HBM.
+// sync[3n .. 3n+2] = {arrivals, flag, departures}: all zero on entry and restored to zero by the last CTA to leave.
+// ------------------------------------------------------------------------------------------------
+constexpr int GNP_MAX_CTAS = 148;  // one CTA per SM; two such launches (2 CTAs of <= 512 threads per SM) stay co-resident
+
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_s32(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct GnPrepParams {
+  const uint16_t* x1;
+  const uint16_t* x2;   // second source of a channel concatenation, or null
+  uint16_t* cat_out;    // raw concatenation [N*H*W, C] or null
+  uint16_t* out;
+  const float* gamma;
+  const float* beta;
+  float* ws;            // [N][chunks][groups][2] partials, then [N][groups][2] mean/rstd at ws_mr
+  float* ws_mr;
+  int* sync;            // [N][3]
+  int N, H, W, C1, C2, ld1, ld2, groups, act, circ_stats, circ, up, phases, halo;
+  int Ho, Wo;
+  float count, eps;
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(512, 2) gn_prep_kernel(const GnPrepParams p) {
+  extern __shared__ float s_acc[];  // phase 1: [ppi][2][C] partials; phase 2: [2][C] scale / shift
+  pdl_launch_dependents();
+  pdl_wait();
+  const int C = p.C1 + p.C2;
+  const int vecs = C / 8, vecs1 = p.C1 / 8;
+  const int ppi = blockDim.x / vecs;
+  const int v = threadIdx.x % vecs, pl = threadIdx.x / vecs;
+  const int n = blockIdx.y, chunks = gridDim.x;
+  const int hw = p.H * p.W;
+  const bool second = v >= vecs1;
+  const uint16_t* src = second ? p.x2 + (size_t)n * hw * p.ld2 + (v - vecs1) * 8 : p.x1 + (size_t)n * hw * p.ld1 + v * 8;
+  const int ld = second ? p.ld2 : p.ld1;
+  const bool active = pl < ppi;     // blockDim.x is a multiple of vecs, so every thread is active; kept for clarity
+  // ---------------- phase 1: statistics of this CTA's band of source pixels ----------------
+  {
+    const int per = (hw + chunks - 1) / chunks;
+    const int p_begin = blockIdx.x * per, p_end = min(hw, p_begin + per);
+    float s[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+    auto accum = [&](const uint4& raw, int px) {
+      float wgt = 1.f;
+      if (p.circ_stats > 0) {
+        const int col = px % p.W;
+        wgt += (col < p.circ_stats ? 1.f : 0.f) + (col >= p.W - p.circ_stats ? 1.f : 0.f);
+      }
+      const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack2<BF16>(w4[e]);
+        s[2 * e] += wgt * f.x;
+        q[2 * e] += wgt * f.x * f.x;
+        s[2 * e + 1] += wgt * f.y;
+        q[2 * e + 1] += wgt * f.y * f.y;
+      }
+      if (p.cat_out) *reinterpret_cast<uint4*>(p.cat_out + ((size_t)n * hw + px) * C + v * 8) = raw;
+    };
+    if (active) {
+      int px = p_begin + pl;
+      for (; px + 3 * ppi < p_end; px += 4 * ppi) {
+        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(src + (size_t)px * ld));
+        const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(px + ppi) * ld));
+        const uint4 r2 = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(px + 2 * ppi) * ld));
+        const uint4 r3 = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(px + 3 * ppi) * ld));
+        accum(r0, px);
+        accum(r1, px + ppi);
+        accum(r2, px + 2 * ppi);
+        accum(r3, px + 3 * ppi);
+      }
+      for (; px < p_end; px += ppi) accum(__ldg(reinterpret_cast<const uint4*>(src + (size_t)px * ld)), px);
+      float* mine = s_acc + (size_t)pl * 2 * C;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        mine[v * 8 + e] = s[e];
+        mine[C + v * 8 + e] = q[e];
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float a = s_acc[i];
+    for (int l = 1; l < ppi; ++l) a += s_acc[(size_t)l * 2 * C + i];
+    s_acc[i] = a;
+  }
+  __syncthreads();
+  const int cpg = C / p.groups;
+  for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      a += s_acc[c];
+      b += s_acc[C + c];
+    }
+    float* o = p.ws + (((size_t)n * chunks + blockIdx.x) * p.groups + g) * 2;
+    o[0] = a;
+    o[1] = b;
+  }
+  // ---------------- per-image barrier ----------------
+  int* sync = p.sync + 3 * n;
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&sync[0], 1) == chunks - 1);
+  __syncthreads();
+  float* mr = p.ws_mr + (size_t)n * p.groups * 2;
+  if (s_last) {
+    __threadfence();
+    for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
+      double a = 0.0, b = 0.0;
+      for (int c = 0; c < chunks; ++c) {
+        const float* o = p.ws + (((size_t)n * chunks + c) * p.groups + g) * 2;
+        a += __ldcg(o);
+        b += __ldcg(o + 1);
+      }
+      const double mean = a / p.count;
+      double var = b / p.count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      mr[g * 2 + 0] = float(mean);
+      mr[g * 2 + 1] = float(1.0 / sqrt(var + double(p.eps)));
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_s32(&sync[1], 1);
+  } else {
+    if (threadIdx.x == 0) {
+      unsigned spins = 0;
+      while (ld_acquire_s32(&sync[1]) == 0) {
+        __nanosleep(40);
+        if (++spins > (1u << 26)) {  // ~3 s: a lost CTA is a bug (grid larger than the co-resident capacity)
+          printf("pf gn_prep_kernel: image barrier timed out (block %d,%d)\n", blockIdx.x, blockIdx.y);
+          __trap();
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // scale / shift of this image into shared memory (aliases the phase-1 partials)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mean = __ldcg(mr + g * 2), rstd = __ldcg(mr + g * 2 + 1);
+    const float sc = rstd * __ldg(p.gamma + c);
+    s_acc[c] = sc;
+    s_acc[C + c] = __ldg(p.beta + c) - mean * sc;
+  }
+  __syncthreads();
+  // everyone has read mean / rstd: the last CTA to get here re-arms the image's barrier for the next launch
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&sync[2], 1) == chunks - 1) {
+      sync[0] = 0;
+      sync[2] = 0;
+      st_release_s32(&sync[1], 0);
+    }
+  }
+  // ---------------- phase 2: this CTA's share of the image's output positions ----------------
+  const int We = p.W + 2 * p.circ;
+  const int Hu = p.H * p.up, Wu = We * p.up;
+  const int total = p.phases * p.Ho * p.Wo;
+  const int per_o = (total + chunks - 1) / chunks;
+  const int o_begin = blockIdx.x * per_o, o_end = min(total, o_begin + per_o);
+  const float4 s0 = *reinterpret_cast<const float4*>(s_acc + v * 8), s1 = *reinterpret_cast<const float4*>(s_acc + v * 8 + 4);
+  const float4 h0 = *reinterpret_cast<const float4*>(s_acc + C + v * 8), h1 = *reinterpret_cast<const float4*>(s_acc + C + v * 8 + 4);
+  const size_t img_out = (size_t)p.Ho * p.Wo;
+  const int hw_o = p.Ho * p.Wo;
+  // (output position) -> (source pixel offset or -1 for the zero halo, output vector pointer)
+  auto locate = [&](int o, long long& soff, uint4*& dst) {
+    const int ph = o / hw_o;
+    const int r = o - ph * hw_o;
+    const int i = r / p.Wo, j = r - i * p.Wo;
+    int yy, xx;
+    if (p.phases == 4) {
+      yy = 2 * i + (ph >> 1) - 1;
+      xx = 2 * j + (ph & 1) - 1;
+    } else {
+      yy = i - p.halo;
+      xx = j - p.halo;
+    }
+    soff = -1;
+    if (yy >= 0 && yy < Hu && xx >= 0 && xx < Wu) {
+      const int sy = yy / p.up;
+      int sx = xx / p.up - p.circ;
+      if (sx < 0) sx += p.W;
+      else if (sx >= p.W) sx -= p.W;
+      soff = ((long long)sy * p.W + sx) * ld;
+    }
+    dst = reinterpret_cast<uint4*>(p.out + (((size_t)ph * p.N + n) * img_out + r) * C + v * 8);  // [phases][N][Ho][Wo][C]
+  };
+  auto finish = [&](const uint4& raw, bool live, uint4* dst) {
+    uint4 outv = make_uint4(0, 0, 0, 0);
+    if (live) {
+      const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = unpack2<BF16>(w4[e]);
+        f[2 * e] = t.x;
+        f[2 * e + 1] = t.y;
+      }
+      f[0] = fmaf(f[0], s0.x, h0.x); f[1] = fmaf(f[1], s0.y, h0.y); f[2] = fmaf(f[2], s0.z, h0.z); f[3] = fmaf(f[3], s0.w, h0.w);
+      f[4] = fmaf(f[4], s1.x, h1.x); f[5] = fmaf(f[5], s1.y, h1.y); f[6] = fmaf(f[6], s1.z, h1.z); f[7] = fmaf(f[7], s1.w, h1.w);
+      if (p.act == PF_ACT_SILU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
+      }
+      outv = make_uint4(pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]), pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
+    }
+    *dst = outv;
+  };
+  const uint4 z4 = make_uint4(0, 0, 0, 0);
+  int o = o_begin + pl;
+  for (; o + 3 * ppi < o_end; o += 4 * ppi) {  // four independent L2 loads in flight per thread
+    long long so[4];
+    uint4* dst[4];
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) locate(o + u * ppi, so[u], dst[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) raw[u] = so[u] >= 0 ? __ldcg(reinterpret_cast<const uint4*>(src + so[u])) : z4;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) finish(raw[u], so[u] >= 0, dst[u]);
+  }
+  for (; o < o_end; o += ppi) {
+    long long so;
+    uint4* dst;
+    locate(o, so, dst);
+    const uint4 raw = so >= 0 ? __ldcg(reinterpret_cast<const uint4*>(src + so)) : z4;
+    finish(raw, so >= 0, dst);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm(x + pe): one warp per token, two-pass in registers
 // ------------------------------------------------------------------------------------------------
 template <bool BF16, int MAXV>
@@ -364,6 +611,68 @@ extern "C" int pf_conv_prep(const void* x, void* out, int dtype, int N, int H, i
   if (dtype == PF_BF16) launch_pdl(conv_prep_kernel<true>, grid, dim3(256), smem, st, p);
   else launch_pdl(conv_prep_kernel<false>, grid, dim3(256), smem, st, p);
   PF_CHECK_LAUNCH("conv_prep_kernel");
+  return PF_OK;
+}
+
+extern "C" int pf_gn_prep_ws_floats(int N, int groups) {
+  return N * pf::GNP_MAX_CTAS * groups * 2 + N * groups * 2;
+}
+
+extern "C" int pf_gn_prep(const void* x1, int ld1, int C1, const void* x2, int ld2, int C2, void* cat_out, void* out,
+                          int dtype, int N, int H, int W, int groups, float eps, const float* gamma, const float* beta,
+                          int act, int circ_stats, int circ, int up, int phases, int halo, float* ws, int* sync,
+                          void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(x1 && out && gamma && beta && ws && sync, "pf_gn_prep: null pointer");
+  PF_CHECK_ARG(dtype == PF_BF16 || dtype == PF_F16, "pf_gn_prep: 16-bit dtype required");
+  if (!x2) C2 = 0;
+  const int C = C1 + C2;
+  PF_CHECK_ARG(N > 0 && N <= GNP_MAX_CTAS && H > 0 && W > 0 && C1 > 0 && C1 % 8 == 0 && C2 % 8 == 0 && ld1 % 8 == 0 &&
+                   ld1 >= C1 && (!x2 || (ld2 % 8 == 0 && ld2 >= C2 && C2 > 0)) && groups > 0 && C % groups == 0 &&
+                   C / 8 <= 512,
+               "pf_gn_prep: bad shape N=%d H=%d W=%d C1=%d C2=%d groups=%d", N, H, W, C1, C2, groups);
+  PF_CHECK_ARG(!cat_out || x2, "pf_gn_prep: cat_out needs a second source");
+  PF_CHECK_ARG(act == PF_ACT_NONE || act == PF_ACT_SILU, "pf_gn_prep: act must be none or silu");
+  PF_CHECK_ARG((up == 1 || up == 2) && (phases == 1 || phases == 4) && (halo == 0 || halo == 1) && circ >= 0 && circ <= W &&
+                   circ_stats >= 0 && circ_stats <= W,
+               "pf_gn_prep: bad geometry up=%d phases=%d halo=%d circ=%d", up, phases, halo, circ);
+  PF_CHECK_ARG(!(phases == 4 && (up != 1 || halo != 1 || (H % 2) || ((W + 2 * circ) % 2))),
+               "pf_gn_prep: stride-2 phase split needs up=1, halo=1 and even extents");
+  GnPrepParams p;
+  p.x1 = static_cast<const uint16_t*>(x1);
+  p.x2 = static_cast<const uint16_t*>(x2);
+  p.cat_out = static_cast<uint16_t*>(cat_out);
+  p.out = static_cast<uint16_t*>(out);
+  p.gamma = gamma; p.beta = beta;
+  p.ws = ws;
+  p.ws_mr = ws + (size_t)N * GNP_MAX_CTAS * groups * 2;
+  p.sync = sync;
+  p.N = N; p.H = H; p.W = W; p.C1 = C1; p.C2 = C2; p.ld1 = ld1; p.ld2 = x2 ? ld2 : ld1; p.groups = groups; p.act = act;
+  p.circ_stats = circ_stats; p.circ = circ; p.up = up; p.phases = phases; p.halo = halo;
+  const int Hu = H * up, Wu = (W + 2 * circ) * up;
+  if (phases == 4) {
+    p.Ho = Hu / 2 + 1;
+    p.Wo = Wu / 2 + 1;
+  } else {
+    p.Ho = Hu + 2 * halo;
+    p.Wo = Wu + 2 * halo;
+  }
+  p.count = float(H) * float(W + 2 * circ_stats) * float(C / groups);
+  p.eps = eps;
+  const int hw = H * W;
+  int chunks = hw / 16;  // >= 16 source pixels per CTA
+  const int cap = GNP_MAX_CTAS / N;
+  chunks = chunks < 1 ? 1 : (chunks > cap ? cap : chunks);
+  const int vecs = C / 8;
+  int ppi = 512 / vecs;
+  if (ppi < 1) ppi = 1;
+  const int threads = vecs * ppi;
+  const size_t smem = 2 * (size_t)C * ppi * sizeof(float);  // <= 32 KB
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(chunks, N);
+  if (dtype == PF_BF16) launch_pdl(gn_prep_kernel<true>, grid, dim3(threads), smem, st, p);
+  else launch_pdl(gn_prep_kernel<false>, grid, dim3(threads), smem, st, p);
+  PF_CHECK_LAUNCH("gn_prep_kernel");
   return PF_OK;
 }
 

@@ -53,6 +53,31 @@ class _Lin:
         self.n, self.k = self.w.shape
 
 
+# LayerNorm folded into the consumer GEMM (ops.gemm_taps ln=...): A/B switch for debugging / the unfused-path tests
+FUSE_LN = __import__("os").environ.get("PF_FUSE_LN", "1") != "0"
+# GroupNorm statistics + apply + layout as ONE launch (ops.gn_prep) instead of pf_groupnorm_stats -> pf_conv_prep, and the
+# skip concatenation folded into it; same A/B switch idea
+FUSE_GN = __import__("os").environ.get("PF_FUSE_GN", "1") != "0"
+
+
+class _LinLN:
+    """nn.Linear applied to LayerNorm(x): W' = gamma * W (16-bit), colsum[n] = sum_k W'[n,k] of the ROUNDED weights (so the
+    mean term cancels exactly), bias' = W beta + b. `geglu_bn` packs W' for the GEGLU epilogue (value|gate per tile)."""
+
+    def __init__(self, w: Tensor, b: Optional[Tensor], norm, dev, dt, geglu_bn: int = 0):
+        w64 = w.detach().double().reshape(w.shape[0], -1)
+        g, be = norm.weight.detach().double().to(w64.device), norm.bias.detach().double().to(w64.device)
+        wp = (w64 * g[None, :]).float()
+        bp = (w64 @ be + (b.detach().double() if b is not None else 0.0)).float()
+        if geglu_bn:
+            wp, bp = pack_geglu(wp, bp, geglu_bn)
+        self.w = wp.to(dev, dt).contiguous()
+        self.b = bp.to(dev, torch.float32).contiguous()
+        self.colsum = self.w.float().sum(1).contiguous()
+        self.eps = float(norm.eps)
+        self.n, self.k = self.w.shape
+
+
 class _Norm:
     def __init__(self, mod, dev):
         self.g = mod.weight.detach().to(dev, torch.float32).contiguous()
@@ -98,6 +123,10 @@ class _Transformer:
         self.ff1_w, self.ff1_b = wp.to(dev, dt).contiguous(), bp.to(dev)
         self.ff2 = _Lin(ff2.weight, ff2.bias, dev, dt)
         self.C = self.proj_in.n
+        # the three LayerNorms folded into their consumer GEMMs
+        self.qkv_ln = _LinLN(torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0), None, blk.norm1, dev, dt)
+        self.q2_ln = _LinLN(a2.to_q.weight, None, blk.norm2, dev, dt)
+        self.ff1_ln = _LinLN(ff1.weight, ff1.bias, blk.norm3, dev, dt, geglu_bn=self.ff1_bn)
 
 
 class UNetPack:
@@ -228,9 +257,8 @@ class Branch:
     def conv_out(self, x: Img) -> Tensor:
         p = self.p
         c = 1 if self.circ else 0
-        stats = ops.groupnorm_stats(x.t, x.N, x.H, x.W, p.groups, p.norm_out.eps, 0)  # un-padded (MVGenModel.py:288)
-        xp = ops.conv_prep(x.t, x.N, x.H, x.W, stats=stats, gamma=p.norm_out.g, beta=p.norm_out.b, groups=p.groups,
-                           act=ops.PF_ACT_SILU, circ=c, halo=1)
+        xp = self._norm_prep(x.t, x.N, x.H, x.W, p.norm_out, act=ops.PF_ACT_SILU, circ_stats=0, circ=c,
+                             halo=1)  # statistics of the un-padded tensor (MVGenModel.py:288)
         # 3x3 conv as 9 taps (the 64-column tile holds the 4 real output channels + zero padding), fp32 out
         We = x.W + 2 * c
         Hp, Wp = x.H + 2, We + 2
@@ -239,27 +267,44 @@ class Branch:
                       image_map=(Hp, Wp, 1, 1 + c, x.H, x.W), block_n=64)
         return o[:, :p.conv_out_c].reshape(x.N, x.H, x.W, p.conv_out_c).permute(0, 3, 1, 2).contiguous()
 
-    def resnet(self, x: Img, r: _Resnet) -> Img:
-        """ResnetBlock2D; panorama: pad_pano(2) -> block -> unpad_pano(2) (MVGenModel.py:110-115)."""
+    def _norm_prep(self, xt: Tensor, N: int, H: int, W: int, norm: _Norm, *, act: int, circ_stats: int, circ: int,
+                   halo: int) -> Tensor:
+        """GroupNorm (+SiLU) of a token tensor into the tap-GEMM A layout: one fused launch, or the two-kernel path."""
+        g = self.p.groups
+        if FUSE_GN:
+            return ops.gn_prep(xt, N, H, W, gamma=norm.g, beta=norm.b, groups=g, eps=norm.eps, act=act,
+                               circ_stats=circ_stats, circ=circ, halo=halo)
+        st = ops.groupnorm_stats(xt, N, H, W, g, norm.eps, circ_stats)
+        return ops.conv_prep(xt, N, H, W, stats=st, gamma=norm.g, beta=norm.b, groups=g, act=act, circ=circ, halo=halo)
+
+    def resnet(self, x: Img, r: _Resnet, skip: Optional[Img] = None) -> Img:
+        """ResnetBlock2D; panorama: pad_pano(2) -> block -> unpad_pano(2) (MVGenModel.py:110-115). `skip`: the decoder's
+        torch.cat([hidden, skip], dim=1) input (MVGenModel.py:223,231,246,254)."""
         c = 2 if self.circ else 0
         N, H, W = x.N, x.H, x.W
         We = W + 2 * c
         g = self.p.groups
-        s1 = ops.groupnorm_stats(x.t, N, H, W, g, r.norm1.eps, c)
-        a1 = ops.conv_prep(x.t, N, H, W, stats=s1, gamma=r.norm1.g, beta=r.norm1.b, groups=g, act=ops.PF_ACT_SILU,
-                           circ=c, halo=1)
+        xt = x.t
+        if skip is not None:  # torch.cat([hidden, skip], 1) (MVGenModel.py:223,231): folded into the norm1 launch
+            if FUSE_GN:
+                a1, xt = ops.gn_prep(x.t, N, H, W, gamma=r.norm1.g, beta=r.norm1.b, groups=g, eps=r.norm1.eps,
+                                     act=ops.PF_ACT_SILU, circ_stats=c, circ=c, halo=1, x2=skip.t, want_cat=True)
+            else:
+                xt = self.concat(x, skip).t
+                a1 = self._norm_prep(xt, N, H, W, r.norm1, act=ops.PF_ACT_SILU, circ_stats=c, circ=c, halo=1)
+        else:
+            a1 = self._norm_prep(xt, N, H, W, r.norm1, act=ops.PF_ACT_SILU, circ_stats=c, circ=c, halo=1)
         Hp, Wp = H + 2, We + 2
         h1 = torch.empty((N * H * We, r.conv1.cout), dtype=self.dt, device=x.t.device)
         ops.gemm_taps(a1, r.conv1.w, h1, M=N * Hp * Wp, Kc=r.conv1.cin, taps=taps3x3(Wp), bias=r.conv1.b,
                       rowbias=self.temb[:, r.temb_off:r.temb_off + r.conv1.cout], image_map=(Hp, Wp, 1, 1, H, We))
-        s2 = ops.groupnorm_stats(h1, N, H, We, g, r.norm2.eps, 0)  # the padded-width tensor, borders included
-        a2 = ops.conv_prep(h1, N, H, We, stats=s2, gamma=r.norm2.g, beta=r.norm2.b, groups=g, act=ops.PF_ACT_SILU,
-                           circ=0, halo=1)
+        # norm2 sees the padded-width tensor, borders included
+        a2 = self._norm_prep(h1, N, H, We, r.norm2, act=ops.PF_ACT_SILU, circ_stats=0, circ=0, halo=1)
         if r.short is not None:
             res = torch.empty((N * H * W, r.short.n), dtype=self.dt, device=x.t.device)
-            ops.gemm_taps(x.t, r.short.w, res, M=N * H * W, Kc=r.short.k, bias=r.short.b)
+            ops.gemm_taps(xt, r.short.w, res, M=N * H * W, Kc=r.short.k, bias=r.short.b)
         else:
-            res = x.t
+            res = xt
         out = torch.empty((N * H * W, r.conv2.cout), dtype=self.dt, device=x.t.device)
         ops.gemm_taps(a2, r.conv2.w, out, M=N * Hp * Wp, Kc=r.conv2.cin, taps=taps3x3(Wp), bias=r.conv2.b,
                       residual=res, image_map=(Hp, Wp, 1, 1 + c, H, W))
@@ -271,27 +316,43 @@ class Branch:
         L, T = H * W, N * H * W
         dev, dt = x.t.device, self.dt
         new = lambda n: torch.empty((T, n), dtype=dt, device=dev)
-        s = ops.groupnorm_stats(x.t, N, H, W, self.p.groups, t.norm.eps, 0)
-        xn = ops.conv_prep(x.t, N, H, W, stats=s, gamma=t.norm.g, beta=t.norm.b, groups=self.p.groups, halo=0)
-        h = ops.gemm_taps(xn, t.proj_in.w, new(C), M=T, Kc=t.proj_in.k, bias=t.proj_in.b)
+        xn = self._norm_prep(x.t, N, H, W, t.norm, act=ops.PF_ACT_NONE, circ_stats=0, circ=0, halo=0)
         d = C // t.heads
-        # self attention
-        n1 = ops.layernorm(h, t.ln1.g, t.ln1.b, t.ln1.eps)
-        qkv = ops.gemm_taps(n1, t.qkv.w, new(3 * C), M=T, Kc=C).reshape(N, L, 3 * C)
-        o = torch.empty((N, L, C), dtype=dt, device=dev)
-        ops.fmha(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], o, heads=t.heads, head_dim=d, scale=d ** -0.5)
-        h = ops.gemm_taps(o.reshape(T, C), t.out1.w, new(C), M=T, Kc=C, bias=t.out1.b, residual=h)
-        # text cross attention (K/V precomputed by set_text)
-        n2 = ops.layernorm(h, t.ln2.g, t.ln2.b, t.ln2.eps)
-        q = ops.gemm_taps(n2, t.q2.w, new(C), M=T, Kc=C).reshape(N, L, C)
         kv = self.text_kv
-        ops.fmha(q, kv[..., t.kv_off:t.kv_off + C], kv[..., t.kv_off + C:t.kv_off + 2 * C], o, heads=t.heads,
-                 head_dim=d, scale=d ** -0.5)
-        h = ops.gemm_taps(o.reshape(T, C), t.out2.w, new(C), M=T, Kc=C, bias=t.out2.b, residual=h)
-        # feed-forward
-        n3 = ops.layernorm(h, t.ln3.g, t.ln3.b, t.ln3.eps)
-        f = ops.gemm_taps(n3, t.ff1_w, new(t.ff2.k), M=T, Kc=C, bias=t.ff1_b, act=ops.PF_ACT_GEGLU, block_n=t.ff1_bn)
-        h = ops.gemm_taps(f, t.ff2.w, new(C), M=T, Kc=t.ff2.k, bias=t.ff2.b, residual=h)
+        o = torch.empty((N, L, C), dtype=dt, device=dev)
+        if FUSE_LN:
+            # every LayerNorm is folded into its consumer: the producer GEMM emits per-row (sum, sum^2) partials, the
+            # consumer (gamma-scaled weights) normalises in its epilogue — the normalised tensor is never stored
+            h, st = ops.gemm_taps(xn, t.proj_in.w, new(C), M=T, Kc=t.proj_in.k, bias=t.proj_in.b, row_stats=True)
+            qkv = ops.gemm_taps(h, t.qkv_ln.w, new(3 * C), M=T, Kc=C, bias=t.qkv_ln.b,
+                                ln=(st, t.qkv_ln.colsum, t.qkv_ln.eps)).reshape(N, L, 3 * C)
+            ops.fmha(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], o, heads=t.heads, head_dim=d, scale=d ** -0.5)
+            h, st = ops.gemm_taps(o.reshape(T, C), t.out1.w, new(C), M=T, Kc=C, bias=t.out1.b, residual=h, row_stats=True)
+            q = ops.gemm_taps(h, t.q2_ln.w, new(C), M=T, Kc=C, bias=t.q2_ln.b,
+                              ln=(st, t.q2_ln.colsum, t.q2_ln.eps)).reshape(N, L, C)
+            ops.fmha(q, kv[..., t.kv_off:t.kv_off + C], kv[..., t.kv_off + C:t.kv_off + 2 * C], o, heads=t.heads,
+                     head_dim=d, scale=d ** -0.5)
+            h, st = ops.gemm_taps(o.reshape(T, C), t.out2.w, new(C), M=T, Kc=C, bias=t.out2.b, residual=h, row_stats=True)
+            f = ops.gemm_taps(h, t.ff1_ln.w, new(t.ff2.k), M=T, Kc=C, bias=t.ff1_ln.b, act=ops.PF_ACT_GEGLU,
+                              block_n=t.ff1_bn, ln=(st, t.ff1_ln.colsum, t.ff1_ln.eps))
+            h = ops.gemm_taps(f, t.ff2.w, new(C), M=T, Kc=t.ff2.k, bias=t.ff2.b, residual=h)
+        else:
+            h = ops.gemm_taps(xn, t.proj_in.w, new(C), M=T, Kc=t.proj_in.k, bias=t.proj_in.b)
+            # self attention
+            n1 = ops.layernorm(h, t.ln1.g, t.ln1.b, t.ln1.eps)
+            qkv = ops.gemm_taps(n1, t.qkv.w, new(3 * C), M=T, Kc=C).reshape(N, L, 3 * C)
+            ops.fmha(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], o, heads=t.heads, head_dim=d, scale=d ** -0.5)
+            h = ops.gemm_taps(o.reshape(T, C), t.out1.w, new(C), M=T, Kc=C, bias=t.out1.b, residual=h)
+            # text cross attention (K/V precomputed by set_text)
+            n2 = ops.layernorm(h, t.ln2.g, t.ln2.b, t.ln2.eps)
+            q = ops.gemm_taps(n2, t.q2.w, new(C), M=T, Kc=C).reshape(N, L, C)
+            ops.fmha(q, kv[..., t.kv_off:t.kv_off + C], kv[..., t.kv_off + C:t.kv_off + 2 * C], o, heads=t.heads,
+                     head_dim=d, scale=d ** -0.5)
+            h = ops.gemm_taps(o.reshape(T, C), t.out2.w, new(C), M=T, Kc=C, bias=t.out2.b, residual=h)
+            # feed-forward
+            n3 = ops.layernorm(h, t.ln3.g, t.ln3.b, t.ln3.eps)
+            f = ops.gemm_taps(n3, t.ff1_w, new(t.ff2.k), M=T, Kc=C, bias=t.ff1_b, act=ops.PF_ACT_GEGLU, block_n=t.ff1_bn)
+            h = ops.gemm_taps(f, t.ff2.w, new(C), M=T, Kc=t.ff2.k, bias=t.ff2.b, residual=h)
         out = ops.gemm_taps(h, t.proj_out.w, new(x.C), M=T, Kc=C, bias=t.proj_out.b, residual=x.t)
         return Img(out, N, H, W)
 

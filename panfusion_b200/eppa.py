@@ -15,7 +15,8 @@ import torch.nn as nn
 from torch import Tensor
 
 from . import geometry, ops
-from .engine import Img, _Lin, _Norm, img_from_nchw
+from . import engine
+from .engine import Img, _Lin, _LinLN, _Norm, img_from_nchw
 from .packing import pack_geglu
 
 
@@ -190,6 +191,7 @@ class WarpAttn(nn.Module):
             out=_Lin(a.to_out.weight, a.to_out.bias, dev, dt),
             ff1_w=wp.to(dev, dt).contiguous(), ff1_b=bp.to(dev), ff1_bn=bn,
             ff2=_Lin(t.ff.net[2].weight, t.ff.net[2].bias, dev, dt),
+            ff1_ln=_LinLN(t.ff.net[0].proj.weight, t.ff.net[0].proj.bias, t.norm2, dev, dt, geglu_bn=bn),
             ln1=_Norm(t.norm1, dev), ln2=_Norm(t.norm2, dev), heads=a.heads)
         return self._packed
 
@@ -243,6 +245,12 @@ class WarpAttn(nn.Module):
 
         def finish(o, x_tok, rows):
             # to_out + residual, then x + FF(norm2(x)) (transformer.py:159-160)
+            if engine.FUSE_LN:  # norm2 folded into the GEGLU projection (engine._LinLN)
+                x1, st = ops.gemm_taps(o, w["out"].w, new(rows, C), M=rows, Kc=C, bias=w["out"].b, residual=x_tok,
+                                       row_stats=True)
+                f = ops.gemm_taps(x1, w["ff1_ln"].w, new(rows, 4 * C), M=rows, Kc=C, bias=w["ff1_ln"].b,
+                                  act=ops.PF_ACT_GEGLU, block_n=w["ff1_bn"], ln=(st, w["ff1_ln"].colsum, w["ff1_ln"].eps))
+                return ops.gemm_taps(f, w["ff2"].w, new(rows, C), M=rows, Kc=4 * C, bias=w["ff2"].b, residual=x1)
             x1 = ops.gemm_taps(o, w["out"].w, new(rows, C), M=rows, Kc=C, bias=w["out"].b, residual=x_tok)
             n2 = ops.layernorm(x1, w["ln2"].g, w["ln2"].b, w["ln2"].eps)
             f = ops.gemm_taps(n2, w["ff1_w"], new(rows, 4 * C), M=rows, Kc=C, bias=w["ff1_b"], act=ops.PF_ACT_GEGLU,

@@ -245,11 +245,11 @@ class MultiViewBaseModel(nn.Module):
             for j, pres in enumerate(pblk["resnets"]):
                 if has_pers:
                     blk = pers.p.up[i]
-                    h = pers.resnet(pers.concat(h, skips.pop()), blk["resnets"][j])
+                    h = pers.resnet(h, blk["resnets"][j], skip=skips.pop())
                     if blk["attns"] is not None:
                         h = pers.transformer(h, blk["attns"][j])
                 with torch.cuda.stream(side):
-                    p = pano.resnet(pano.concat(p, pano_skips.pop()), pres)
+                    p = pano.resnet(p, pres, skip=pano_skips.pop())
                     if pblk["attns"] is not None:
                         p = pano.transformer(p, pblk["attns"][j])
             if pblk["up"] is not None:

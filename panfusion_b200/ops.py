@@ -56,11 +56,15 @@ def pick_block_n(n: int, act: int = PF_ACT_NONE) -> int:
 def gemm_taps(A: Tensor, B: Tensor, out: Tensor, *, M: int, Kc: int, taps: Sequence[int] = (0,),
               bias: Optional[Tensor] = None, rowbias: Optional[Tensor] = None, rows_per_group: int = 0,
               residual: Optional[Tensor] = None, act: int = PF_ACT_NONE,
-              image_map: Optional[tuple] = None, block_n: int = 0, k_splits: Optional[int] = None) -> Tensor:
+              image_map: Optional[tuple] = None, block_n: int = 0, k_splits: Optional[int] = None,
+              row_stats: bool = False, ln: Optional[tuple] = None):
     """acc = sum_t A[m + taps[t], :Kc] @ B[:, t*Kc:(t+1)*Kc]^T ; see include/panfusion_b200.h (pf_gemm_taps).
 
     A: [a_rows, a_ld] 16-bit, B: [N, len(taps)*Kc] 16-bit packed weight, out: [rows, n_out].
     image_map = (Hm, Wm, i0, j0, Hout, Wout) selects map_mode 1.
+    Fused LayerNorm (see pf_gemm_args): row_stats=True makes this GEMM a PRODUCER — returns (out, stats) with
+    stats [M, slots, 2] fp32 partial (sum, sum of squares) per output row; ln=(stats, colsum, eps) makes it a CONSUMER
+    whose B holds gamma-scaled weights (engine._LinLN).
     """
     _lib.require_cuda(A, B, out)
     assert A.dim() == 2 and B.dim() == 2 and out.dim() == 2
@@ -96,9 +100,19 @@ def gemm_taps(A: Tensor, B: Tensor, out: Tensor, *, M: int, Kc: int, taps: Seque
     if image_map is not None:
         a.map_mode = 1
         a.Hm, a.Wm, a.i0, a.j0, a.Hout, a.Wout = (int(v) for v in image_map)
+    stats = None
+    if row_stats:
+        slots = int(_lib.lib().pf_gemm_row_stats_slots(C.byref(a)))
+        stats = torch.empty((int(M), slots, 2), dtype=torch.float32, device=A.device)
+        a.row_stats_out = stats.data_ptr()
+    if ln is not None:
+        ln_stats, colsum, eps = ln
+        assert ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.shape[0] == int(M)
+        assert colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() == B.shape[0]
+        a.ln_stats, a.ln_slots, a.ln_colsum, a.ln_eps = ln_stats.data_ptr(), ln_stats.shape[1], colsum.data_ptr(), float(eps)
     ws = None
     if k_splits is None:
-        k_splits = _lib.lib().pf_gemm_splitk_plan(C.byref(a)) if SPLIT_K else 1
+        k_splits = _lib.lib().pf_gemm_splitk_plan(C.byref(a)) if (SPLIT_K and not row_stats and ln is None) else 1
     if k_splits > 1:
         a.block_n = int(block_n) & 0xffff  # split-K runs on the tile-per-CTA schedule
         ws = torch.empty(k_splits * int(M) * B.shape[0], dtype=torch.float32, device=A.device)
@@ -106,7 +120,7 @@ def gemm_taps(A: Tensor, B: Tensor, out: Tensor, *, M: int, Kc: int, taps: Seque
         _count(1)
     _count(1)
     _lib.check(_lib.lib().pf_gemm_taps(C.byref(a), _st()))
-    return out
+    return (out, stats) if row_stats else out
 
 
 def bias_tile_flags(bias: Tensor) -> Tensor:
@@ -209,6 +223,30 @@ def conv_prep(x: Tensor, N: int, H: int, W: int, *, stats: Optional[Tensor] = No
     _lib.check(_lib.lib().pf_conv_prep(_vp(x), _vp(out), _lib.dtype_code(x.dtype), N, H, W, Cc, x.stride(0),
                                        _vp(stats), _vp(gamma), _vp(beta), groups, act, circ, up, phases, halo, _st()))
     return out
+
+
+def gn_prep(x: Tensor, N: int, H: int, W: int, *, gamma: Tensor, beta: Tensor, groups: int, eps: float,
+            act: int = PF_ACT_NONE, circ_stats: int = 0, circ: int = 0, up: int = 1, phases: int = 1, halo: int = 1,
+            x2: Optional[Tensor] = None, want_cat: bool = False):
+    """GroupNorm statistics + apply (+SiLU) + conv_prep layout in one launch (pf_gn_prep); with x2 the normalised tensor
+    is the channel concatenation cat(x, x2) and want_cat also returns that raw concatenation.
+    -> out [phases * N * Ho * Wo, C] (and cat [N*H*W, C] if want_cat)."""
+    C1, C2 = x.shape[1], (x2.shape[1] if x2 is not None else 0)
+    Cc = C1 + C2
+    Hu, Wu = H * up, (W + 2 * circ) * up
+    if phases == 4:
+        Ho, Wo = Hu // 2 + 1, Wu // 2 + 1
+    else:
+        Ho, Wo = Hu + 2 * halo, Wu + 2 * halo
+    lib = _lib.lib()
+    out = torch.empty((phases * N * Ho * Wo, Cc), dtype=x.dtype, device=x.device)
+    cat = torch.empty((N * H * W, Cc), dtype=x.dtype, device=x.device) if want_cat else None
+    ws = torch.empty(lib.pf_gn_prep_ws_floats(N, groups), dtype=torch.float32, device=x.device)
+    _count(1)
+    _lib.check(lib.pf_gn_prep(_vp(x), x.stride(0), C1, _vp(x2), x2.stride(0) if x2 is not None else 0, C2, _vp(cat),
+                              _vp(out), _lib.dtype_code(x.dtype), N, H, W, groups, _f(eps), _vp(gamma), _vp(beta), act,
+                              circ_stats, circ, up, phases, halo, _vp(ws), _vp(_gn_counter_slot(x.device, 3 * N)), _st()))
+    return (out, cat) if want_cat else out
 
 
 def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, pe: Optional[Tensor] = None) -> Tensor:

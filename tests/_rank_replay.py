@@ -46,6 +46,14 @@ class ReplayParallel(ViewParallel):
         return sample, pano
 
 
+def _drop_identity_caches(model):
+    """The text K/V cache is keyed on the identity of the caller's (UNSLICED) prompt tensor — per process that is
+    exact, but here every "rank" shares one model object and one prompt tensor while needing a different slice."""
+    for br in model._branches[:2]:
+        if br is not None:
+            br._text_key = None
+
+
 def run_unsharded_recording(model, inputs):
     rec = []
     WarpAttn.kv_tap = lambda kv: rec.append(kv.clone())
@@ -67,6 +75,7 @@ def run_all_ranks(model, inputs, batch_shards, view_shards, recorded):
             for vs in range(view_shards):
                 par = ReplayParallel(batch_shards, view_shards, bs, vs, recorded)
                 model._par = par
+                _drop_identity_caches(model)
                 s, p = model(**inputs)
                 if sample is None:
                     sample, pano = s.clone(), p.clone()
@@ -82,5 +91,6 @@ def run_all_ranks(model, inputs, batch_shards, view_shards, recorded):
                 worst = max(worst, par.worst_local)
     finally:
         model._par = None
+        _drop_identity_caches(model)
     assert not torch.isnan(sample).any() and not torch.isnan(pano).any()
     return sample, pano, worst

@@ -133,3 +133,74 @@ def test_conv3x3_split_k(cuda_device, k_splits):
                   image_map=(Hp, Wp, 1, 1, H, W), k_splits=k_splits)
     got = out.reshape(n, H, W, Cout).permute(0, 3, 1, 2)
     torch.testing.assert_close(got, ref, rtol=1e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,C,N,sched", [(4096 * 10, 320, 960, 0), (300, 640, 640, 0), (130, 1280, 3840, 0),
+                                         (4096 * 10, 320, 320, 1), (777, 640, 1920, 2)])
+def test_layernorm_fused_into_gemm_pair(cuda_device, dtype, M, C, N, sched):
+    """LayerNorm folded around two GEMMs (pf_gemm_args row_stats_out / ln_stats): the producer `x = A W0^T + b0 + res`
+    emits per-row (sum, sum^2) partials, the consumer runs on the UN-normalised x with gamma-scaled weights and
+    normalises in its epilogue. Reference: fp32 torch LayerNorm(x_16bit) -> Linear, i.e. what the stand-alone
+    pf_layernorm + pf_gemm_taps pair computes (diffusers BasicTransformerBlock norm -> to_q|k|v, MVGenModel.py:104)."""
+    from panfusion_b200 import ops
+    from panfusion_b200.engine import _LinLN
+    g = torch.Generator(device="cpu").manual_seed(M + C + N)
+    A = torch.randn(M, C, generator=g).to(dtype).to(cuda_device)
+    W0 = (torch.randn(C, C, generator=g) / C ** 0.5).to(dtype).to(cuda_device)
+    b0 = torch.randn(C, generator=g).to(cuda_device) + 3.0                     # a DC offset: mean >> 0
+    res = (torch.randn(M, C, generator=g) * 2).to(dtype).to(cuda_device)
+    norm = torch.nn.LayerNorm(C)
+    lin = torch.nn.Linear(C, N)
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.3 * torch.randn(C, generator=g))
+        norm.bias.copy_(0.2 * torch.randn(C, generator=g))
+    x = torch.empty(M, C, dtype=dtype, device=cuda_device)
+    x, st = ops.gemm_taps(A, W0, x, M=M, Kc=C, bias=b0, residual=res, row_stats=True, block_n=(sched << 16))
+    xf = x.float()
+    # producer statistics == sums of the (fp32, pre-rounding) rows: compare with the stored 16-bit rows
+    s = st.sum(1)
+    eps16 = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
+    torch.testing.assert_close(s[:, 0], xf.sum(1), rtol=0, atol=eps16 * xf.abs().sum(1).max().item())
+    torch.testing.assert_close(s[:, 1], (xf * xf).sum(1), rtol=4 * eps16, atol=1e-3)
+    p = _LinLN(lin.weight, lin.bias, norm, cuda_device, dtype)
+    out = torch.empty(M, N, dtype=dtype, device=cuda_device)
+    ops.gemm_taps(x, p.w, out, M=M, Kc=C, bias=p.b, ln=(st, p.colsum, p.eps), block_n=(sched << 16))
+    ref = F.linear(F.layer_norm(xf, (C,), norm.weight.to(cuda_device), norm.bias.to(cuda_device), norm.eps),
+                   lin.weight.to(cuda_device), lin.bias.to(cuda_device))
+    # the un-fused path rounds LN(x) to 16 bit before the GEMM; the fused one does not: same error budget
+    err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
+    print(f"[parity] fused LN->linear {dtype} M={M} C={C} N={N}: max err {err:.2e} of max|ref|")
+    assert err < (1.5e-2 if dtype == torch.bfloat16 else 2e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,C,sched", [(4096 * 10, 320, 0), (500, 640, 0), (200, 1280, 1)])
+def test_layernorm_fused_into_geglu(cuda_device, dtype, M, C, sched):
+    """norm3 -> GEGLU projection (diffusers FeedForward; models/modules/transformer.py:8-16,159-160) with the LayerNorm
+    folded into the GEGLU epilogue."""
+    from panfusion_b200 import ops
+    from panfusion_b200.engine import _LinLN
+    g = torch.Generator(device="cpu").manual_seed(M + C)
+    x = (torch.randn(M, C, generator=g) * 1.5 + 0.7).to(dtype).to(cuda_device)
+    W0 = torch.eye(C).to(dtype).to(cuda_device)
+    norm = torch.nn.LayerNorm(C)
+    lin = torch.nn.Linear(C, 8 * C)
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.3 * torch.randn(C, generator=g))
+        norm.bias.copy_(0.2 * torch.randn(C, generator=g))
+    y = torch.empty(M, C, dtype=dtype, device=cuda_device)
+    y, st = ops.gemm_taps(x, W0, y, M=M, Kc=C, row_stats=True)                 # identity producer: y == x
+    assert torch.equal(y, x)
+    bn = ops.pick_block_n(8 * C, ops.PF_ACT_GEGLU)
+    p = _LinLN(lin.weight, lin.bias, norm, cuda_device, dtype, geglu_bn=bn)
+    out = torch.empty(M, 4 * C, dtype=dtype, device=cuda_device)
+    ops.gemm_taps(y, p.w, out, M=M, Kc=C, bias=p.b, act=ops.PF_ACT_GEGLU, block_n=bn | (sched << 16),
+                  ln=(st, p.colsum, p.eps))
+    h = F.linear(F.layer_norm(x.float(), (C,), norm.weight.to(cuda_device), norm.bias.to(cuda_device), norm.eps),
+                 lin.weight.to(cuda_device), lin.bias.to(cuda_device))
+    a, gate = h.chunk(2, dim=-1)
+    ref = a * F.gelu(gate)
+    err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
+    print(f"[parity] fused LN->GEGLU {dtype} M={M} C={C}: max err {err:.2e} of max|ref|")
+    assert err < (1.5e-2 if dtype == torch.bfloat16 else 2e-3)
