@@ -50,6 +50,13 @@ int pf_check_device(void);
 int pf_e2p(const void* src, void* dst, int dtype, int B, int C, int He, int We, int h, int w,
            const double* cams, int cam_stride, int mode, void* stream);
 
+/* e2p of B cameras over B / src_repeat source panoramas: src[B/src_repeat, C, He, We], camera b reads source b / src_repeat
+ * (PanFusion.init_noise, models/pano/PanFusion.py:30-43, expands ONE panorama to its m views before e2p; feature-map
+ * warps of a CFG batch read 2 panoramas from 16 cameras). Same result as pf_e2p on the expanded tensor; the source is read
+ * from HBM once. */
+int pf_e2p_shared(const void* src, void* dst, int dtype, int B, int src_repeat, int C, int He, int We, int h, int w,
+                  const double* cams, int cam_stride, int mode, void* stream);
+
 /* p2e(p_img[B,C,hp,wp]) -> equi[B,C,He,We] (already multiplied by mask), mask[B,1,He,We] uint8 (may be NULL)
  * (p2e.py:52-77; grid math p2e.py:9-49) */
 int pf_p2e(const void* src, void* dst, uint8_t* mask, int dtype, int B, int C, int hp, int wp, int He, int We,
@@ -120,7 +127,8 @@ typedef struct pf_gemm_args {
 } pf_gemm_args;
 
 int pf_gemm_taps(const pf_gemm_args* args, void* stream);
-/* number of column slots a producer with these args writes per row of row_stats_out (depends on the tile width) */
+/* number of column slots a producer with these args writes per row of row_stats_out: 2 per column tile, and a producer's
+ * tile width is a function of N alone (requests / tuning are ignored), so the statistics are bit-identical for any M */
 int pf_gemm_row_stats_slots(const pf_gemm_args* args);
 /* suggested k_splits for this problem (1 = do not split); only M, N, Kc, num_taps, act, map_mode, dtypes are read */
 int pf_gemm_splitk_plan(const pf_gemm_args* args);
@@ -197,7 +205,8 @@ int pf_conv_prep(const void* x, void* out, int dtype, int N, int H, int W, int C
  * The kernel holds a per-image barrier between the statistics and the apply phase (the source is re-read from L2), so its
  * grid is capped at 148 CTAs of <= 512 threads — two such launches (the two UNet branches' streams) are always co-resident.
  * ws: pf_gn_prep_ws_floats(N, groups) floats of scratch; sync: 3*N ints that are ZERO on entry (restored to zero by the
- * kernel; concurrent launches need distinct slots). N <= 148. */
+ * kernel; concurrent launches need distinct slots). The partition of every sum depends on H*W only, never on N: results are
+ * bit-identical for any batch size. */
 int pf_gn_prep_ws_floats(int N, int groups);
 int pf_gn_prep(const void* x1, int ld1, int C1, const void* x2, int ld2, int C2, void* cat_out, void* out, int dtype,
                int N, int H, int W, int groups, float eps, const float* gamma, const float* beta, int act,

@@ -224,7 +224,8 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       if (p.residual) mbar_wait(res_full_bar, 0);
       const uint32_t sw = uint32_t((row >> 1) & 3);  // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
-      float st_s = 0.f, st_q = 0.f;
+      // row statistics in the persistent kernel's order: even 16-column chunks -> slot 0, odd chunks -> slot 1
+      float st_s0 = 0.f, st_s1 = 0.f, st_q0 = 0.f, st_q1 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 16) {
         uint32_t v[16];
@@ -270,10 +271,19 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           f = unpack2<BF16>(r1.w); o[14] += f.x; o[15] += f.y;
         }
         if (p.row_stats) {
+          const bool odd = (c >> 4) & 1;
+          float ss = odd ? st_s1 : st_s0, qq = odd ? st_q1 : st_q0;
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            st_s += o[e];
-            st_q = fmaf(o[e], o[e], st_q);
+            ss += o[e];
+            qq = fmaf(o[e], o[e], qq);
+          }
+          if (odd) {
+            st_s1 = ss;
+            st_q1 = qq;
+          } else {
+            st_s0 = ss;
+            st_q0 = qq;
           }
         }
         *s0 = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]), pack2<BF16>(o[4], o[5]),
@@ -281,10 +291,10 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         *s1 = make_uint4(pack2<BF16>(o[8], o[9]), pack2<BF16>(o[10], o[11]), pack2<BF16>(o[12], o[13]),
                          pack2<BF16>(o[14], o[15]));
       }
-      if (p.row_stats && m < p.M) {  // one thread covers the whole tile row: the second slot of the pair stays zero
+      if (p.row_stats && m < p.M) {
         float2* st = reinterpret_cast<float2*>(p.row_stats) + (long long)m * p.stat_slots + n_tile * 2;
-        st[0] = make_float2(st_s, st_q);
-        st[1] = make_float2(0.f, 0.f);
+        st[0] = make_float2(st_s0, st_q0);
+        st[1] = make_float2(st_s1, st_q1);
       }
       fence_proxy_async_smem();           // generic-proxy writes -> visible to the TMA store
       named_bar_sync(1, 128);             // the four epilogue warps only
@@ -653,6 +663,9 @@ namespace pf {
 // that carries the fused-LayerNorm statistics has no 256-wide variant
 static int resolve_block_n(const pf_gemm_args* a) {
   int bn = (a->block_n & 0xffff) ? (a->block_n & 0xffff) : pf_gemm_pick_block_n(a->N, a->act);
+  // a statistics PRODUCER always uses the width the heuristic derives from N: the slot partition of the row sums (and so
+  // their fp32 rounding) must not depend on M-specific tuning, or a sharded rank would not reproduce the full batch
+  if (a->row_stats_out) bn = pf_gemm_pick_block_n(a->N, a->act);
   if ((a->row_stats_out || a->ln_stats) && a->act != PF_ACT_GEGLU && bn == 256) bn = 128;
   return bn;
 }
@@ -763,7 +776,8 @@ extern "C" int pf_gemm_taps(const pf_gemm_args* a, void* stream) {
   const bool fused_ln = a->row_stats_out || a->ln_stats;
   if (fused_ln) {
     PF_CHECK_ARG(kp.k_splits == 1, "pf_gemm_taps: fused LayerNorm does not combine with split-K");
-    PF_CHECK_ARG(!a->ln_stats || (a->ln_colsum && a->ln_slots > 0 && a->ln_eps > 0.f),
+    PF_CHECK_ARG(!a->ln_stats || (a->ln_colsum && a->ln_slots > 0 && a->ln_slots % 2 == 0 && a->ln_eps > 0.f &&
+                                  (reinterpret_cast<uintptr_t>(a->ln_stats) & 15) == 0),
                  "pf_gemm_taps: ln_stats needs ln_colsum, ln_slots and ln_eps");
     const bool plain16 = a->map_mode == 0 && a->out_dtype == a->dtype && (!a->residual || a->res_dtype == a->dtype) &&
                          (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0;

@@ -210,8 +210,10 @@ __global__ void __launch_bounds__(256) conv_prep_kernel(const PrepParams p) {
 // ------------------------------------------------------------------------------------------------
 // gn_prep: GroupNorm statistics + apply (+SiLU) + conv_prep layout in ONE launch (pf_gn_prep).
 //
-// grid = (chunks, N) with chunks * N <= GNP_MAX_CTAS, so that every CTA of the launch (and of one more such launch on
-// the other branch's stream) is co-resident: the kernel contains a per-image barrier. Phase 1: each CTA sums its band
+// grid = (chunks, G) with chunks * G <= GNP_MAX_CTAS, so that every CTA of the launch (and of one more such launch on
+// the other branch's stream) is co-resident: the kernel contains a per-image barrier. CTA (c, y) serves images
+// y, y + G, ... in turn. `chunks` depends on the image size ONLY, so the order of every floating-point sum — and with it
+// the result, bit for bit — is the same whatever the batch size (a view-sharded rank reproduces the single-GPU run). Phase 1: each CTA sums its band
 // of source pixels per channel (two sources = the skip concatenation torch.cat([hidden, skip], 1), optionally also
 // written out raw), publishes per-group partials, and the LAST CTA of the image to arrive reduces them in a fixed
 // order (deterministic) into mean / rstd and releases the image's flag. Phase 2: after acquiring the flag each CTA
@@ -253,12 +255,14 @@ __global__ void __launch_bounds__(512, 2) gn_prep_kernel(const GnPrepParams p) {
   const int vecs = C / 8, vecs1 = p.C1 / 8;
   const int ppi = blockDim.x / vecs;
   const int v = threadIdx.x % vecs, pl = threadIdx.x / vecs;
-  const int n = blockIdx.y, chunks = gridDim.x;
+  const int chunks = gridDim.x;
   const int hw = p.H * p.W;
   const bool second = v >= vecs1;
-  const uint16_t* src = second ? p.x2 + (size_t)n * hw * p.ld2 + (v - vecs1) * 8 : p.x1 + (size_t)n * hw * p.ld1 + v * 8;
   const int ld = second ? p.ld2 : p.ld1;
   const bool active = pl < ppi;     // blockDim.x is a multiple of vecs, so every thread is active; kept for clarity
+  __shared__ int s_last;
+ for (int n = blockIdx.y; n < p.N; n += gridDim.y) {
+  const uint16_t* src = second ? p.x2 + (size_t)n * hw * p.ld2 + (v - vecs1) * 8 : p.x1 + (size_t)n * hw * p.ld1 + v * 8;
   // ---------------- phase 1: statistics of this CTA's band of source pixels ----------------
   {
     const int per = (hw + chunks - 1) / chunks;
@@ -324,7 +328,6 @@ __global__ void __launch_bounds__(512, 2) gn_prep_kernel(const GnPrepParams p) {
   }
   // ---------------- per-image barrier ----------------
   int* sync = p.sync + 3 * n;
-  __shared__ int s_last;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(&sync[0], 1) == chunks - 1);
@@ -452,6 +455,8 @@ __global__ void __launch_bounds__(512, 2) gn_prep_kernel(const GnPrepParams p) {
     const uint4 raw = so >= 0 ? __ldcg(reinterpret_cast<const uint4*>(src + so)) : z4;
     finish(raw, so >= 0, dst);
   }
+  __syncthreads();  // s_acc (scale / shift) is rewritten by the next image's phase 1
+ }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -627,7 +632,7 @@ extern "C" int pf_gn_prep(const void* x1, int ld1, int C1, const void* x2, int l
   PF_CHECK_ARG(dtype == PF_BF16 || dtype == PF_F16, "pf_gn_prep: 16-bit dtype required");
   if (!x2) C2 = 0;
   const int C = C1 + C2;
-  PF_CHECK_ARG(N > 0 && N <= GNP_MAX_CTAS && H > 0 && W > 0 && C1 > 0 && C1 % 8 == 0 && C2 % 8 == 0 && ld1 % 8 == 0 &&
+  PF_CHECK_ARG(N > 0 && H > 0 && W > 0 && C1 > 0 && C1 % 8 == 0 && C2 % 8 == 0 && ld1 % 8 == 0 &&
                    ld1 >= C1 && (!x2 || (ld2 % 8 == 0 && ld2 >= C2 && C2 > 0)) && groups > 0 && C % groups == 0 &&
                    C / 8 <= 512,
                "pf_gn_prep: bad shape N=%d H=%d W=%d C1=%d C2=%d groups=%d", N, H, W, C1, C2, groups);
@@ -660,16 +665,16 @@ extern "C" int pf_gn_prep(const void* x1, int ld1, int C1, const void* x2, int l
   p.count = float(H) * float(W + 2 * circ_stats) * float(C / groups);
   p.eps = eps;
   const int hw = H * W;
-  int chunks = hw / 16;  // >= 16 source pixels per CTA
-  const int cap = GNP_MAX_CTAS / N;
-  chunks = chunks < 1 ? 1 : (chunks > cap ? cap : chunks);
+  int chunks = hw / 16;  // >= 16 source pixels per CTA; a function of the image size ONLY (batch-invariant sums)
+  chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks);
+  const int gy = N < GNP_MAX_CTAS / chunks ? N : GNP_MAX_CTAS / chunks;
   const int vecs = C / 8;
   int ppi = 512 / vecs;
   if (ppi < 1) ppi = 1;
   const int threads = vecs * ppi;
   const size_t smem = 2 * (size_t)C * ppi * sizeof(float);  // <= 32 KB
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dim3 grid(chunks, N);
+  dim3 grid(chunks, gy);
   if (dtype == PF_BF16) launch_pdl(gn_prep_kernel<true>, grid, dim3(threads), smem, st, p);
   else launch_pdl(gn_prep_kernel<false>, grid, dim3(threads), smem, st, p);
   PF_CHECK_LAUNCH("gn_prep_kernel");

@@ -148,12 +148,183 @@ resample_staged_kernel(const T* __restrict__ src, T* __restrict__ dst, uint8_t* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// quad variant of the staged kernel (the default whenever the output width is a multiple of 4): thread <-> QPT groups
+// of 4 CONSECUTIVE output pixels, so every store is one 16-byte (fp32) / 8-byte (16-bit) vector and a group without
+// any live pixel — ~80 % of a p2e output, whose mask is false outside the camera frustum — costs one predicate and one
+// vector store of zeros per channel. The output plane is cut into tiles of at most 4*QPT*256 pixels (blockIdx.z), so
+// planes of any size keep their source in shared memory. `src_repeat` consecutive batch elements share one source
+// image (B cameras looking at B / src_repeat panoramas: the source is then read once from HBM and again from L2).
+// ---------------------------------------------------------------------------------------------------
+template <typename T> struct Quad;
+template <> struct Quad<float> {
+  static __device__ __forceinline__ void store(float* p, const float* o) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(o[0], o[1], o[2], o[3]));
+  }
+};
+template <> struct Quad<__half> {
+  static __device__ __forceinline__ void store(__half* p, const float* o) {
+    const __half2 a = __floats2half2_rn(o[0], o[1]), b = __floats2half2_rn(o[2], o[3]);
+    __stcs(reinterpret_cast<uint2*>(p), make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b)));
+  }
+};
+template <> struct Quad<__nv_bfloat16> {
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* o) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b = __floats2bfloat162_rn(o[2], o[3]);
+    __stcs(reinterpret_cast<uint2*>(p), make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b)));
+  }
+};
+
+template <typename T, bool P2E, int QPT>
+__global__ void __launch_bounds__(STG_THREADS, 2)
+resample_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, uint8_t* __restrict__ mask_out, int C,
+                     int Hs, int Ws, int Hd, int Wd, const double* __restrict__ cams, int cam_stride, int mode,
+                     int ch_per_cta, int ch_per_stage, int src_repeat, int tile_px) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  const int splane = Hs * Ws, dplane = Hd * Wd;
+  const uint32_t stage_bytes = uint32_t(ch_per_stage) * splane * sizeof(T);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  T* buf0 = reinterpret_cast<T*>(smem + 128);
+  T* buf1 = reinterpret_cast<T*>(smem + 128 + ((stage_bytes + 127) & ~127u));
+
+  const int b = blockIdx.y;
+  const int c_begin = blockIdx.x * ch_per_cta;
+  const int c_end = min(C, c_begin + ch_per_cta);
+  const int n_stages = (c_end - c_begin + ch_per_stage - 1) / ch_per_stage;
+  const int pix0 = blockIdx.z * tile_px;
+  const int pix_end = min(dplane, pix0 + tile_px);
+  const T* sbase = src + (size_t)(b / src_repeat) * C * splane;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int st) {
+    const int ca = c_begin + st * ch_per_stage;
+    const int nch = min(ch_per_stage, c_end - ca);
+    const uint32_t bytes = uint32_t(nch) * splane * sizeof(T);
+    mbar_expect_tx(&bars[st & 1], bytes);
+    bulk_load_1d((st & 1) ? buf1 : buf0, sbase + (size_t)ca * splane, bytes, &bars[st & 1]);
+  };
+  if (threadIdx.x == 0) {
+    issue(0);
+    if (n_stages > 1) issue(1);
+  }
+
+  const double* cam = cams + (size_t)b * cam_stride * PF_CAM_DOUBLES;
+  Taps taps[QPT][4];
+  bool any_live[QPT];
+#pragma unroll
+  for (int i = 0; i < QPT; ++i) {
+    const int q0 = pix0 + 4 * (threadIdx.x + i * STG_THREADS);
+    any_live[i] = false;
+    uint32_t mbits = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pix = q0 + j;
+      bool live = pix < pix_end;
+      float px = 0.f, py = 0.f;
+      if (live) {
+        const int r = pix / Wd, c = pix - r * Wd;
+        if constexpr (P2E) {
+          bool m;
+          p2e_grid(cam, r, c, Hd, Wd, Hs, Ws, px, py, m);
+          live = m;
+          mbits |= (m ? 1u : 0u) << (8 * j);
+        } else {
+          e2p_grid(cam, r, c, Hd, Wd, Hs, Ws, px, py);
+        }
+      }
+      make_taps(px, py, Hs, Ws, mode, live, taps[i][j]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) any_live[i] = any_live[i] || taps[i][j].idx[k] >= 0;
+    }
+    if constexpr (P2E) {
+      if (mask_out && blockIdx.x == 0 && q0 < pix_end)
+        *reinterpret_cast<uint32_t*>(mask_out + (size_t)b * dplane + q0) = mbits;
+    }
+  }
+
+  for (int st = 0; st < n_stages; ++st) {
+    mbar_wait(&bars[st & 1], (st >> 1) & 1);
+    const T* sb = (st & 1) ? buf1 : buf0;
+    const int ca = c_begin + st * ch_per_stage;
+    const int nch = min(ch_per_stage, c_end - ca);
+    T* dp = dst + ((size_t)b * C + ca) * dplane;
+    for (int ch = 0; ch < nch; ++ch) {
+      const T* sp = sb + (size_t)ch * splane;
+#pragma unroll
+      for (int i = 0; i < QPT; ++i) {
+        const int q0 = pix0 + 4 * (threadIdx.x + i * STG_THREADS);
+        if (q0 < pix_end) {
+          float o[4] = {0.f, 0.f, 0.f, 0.f};
+          if (any_live[i]) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (taps[i][j].idx[k] >= 0)
+                  o[j] = __fadd_rn(o[j], __fmul_rn(Cvt<T>::to_f(sp[taps[i][j].idx[k]]), taps[i][j].w[k]));
+              }
+            }
+          }
+          Quad<T>::store(dp + (size_t)ch * dplane + q0, o);
+        }
+      }
+    }
+    __syncthreads();  // everyone done with this buffer before it is refilled
+    if (threadIdx.x == 0 && st + 2 < n_stages) issue(st + 2);
+  }
+}
+
 template <typename T, bool P2E>
 static int launch_resample(const void* src, void* dst, uint8_t* mask, int B, int C, int Hs, int Ws, int Hd, int Wd,
-                           const double* cams, int cam_stride, int mode, cudaStream_t st) {
+                           const double* cams, int cam_stride, int mode, int src_repeat, cudaStream_t st) {
   const int dplane = Hd * Wd;
   const size_t plane_bytes = (size_t)Hs * Ws * sizeof(T);
   const bool aligned = (plane_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  // quad path: vector stores need a 4-pixel-aligned output plane; the mask is written 4 bytes at a time
+  if (aligned && plane_bytes <= 48 * 1024 && C >= 4 && Wd % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 &&
+      (!mask || (reinterpret_cast<uintptr_t>(mask) & 3) == 0) && B <= 65535) {
+    int ch_per_stage = (int)((48 * 1024) / plane_bytes);
+    if (ch_per_stage > 16) ch_per_stage = 16;
+    const int max_tile = 4 * 2 * STG_THREADS;  // QPT = 2
+    const int tiles = (dplane + max_tile - 1) / max_tile;
+    int tile_px = (dplane + tiles - 1) / tiles;
+    tile_px = (tile_px + 3) & ~3;
+    const int qpt = (tile_px + 4 * STG_THREADS - 1) / (4 * STG_THREADS);
+    // exactly ONE wave of co-resident CTAs (2 per SM) when the problem allows it
+    int ctas_per_bt = (148 * 2) / (B * tiles);
+    if (ctas_per_bt < 1) ctas_per_bt = 1;
+    int ch_per_cta = (C + ctas_per_bt - 1) / ctas_per_bt;
+    ch_per_cta = ((ch_per_cta + ch_per_stage - 1) / ch_per_stage) * ch_per_stage;
+    const int grid_x = (C + ch_per_cta - 1) / ch_per_cta;
+    const size_t stage_bytes = ((size_t)ch_per_stage * plane_bytes + 127) & ~size_t(127);
+    const size_t smem = 128 + 128 + 2 * stage_bytes;
+    dim3 grid(grid_x, B, tiles);
+#define PF_LAUNCH_QUAD(QPT)                                                                                       \
+  {                                                                                                               \
+    auto kern = resample_quad_kernel<T, P2E, QPT>;                                                                \
+    int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),       \
+                        "cudaFuncSetAttribute(resample)");                                                        \
+    if (rc) return rc;                                                                                            \
+    kern<<<grid, STG_THREADS, smem, st>>>(static_cast<const T*>(src), static_cast<T*>(dst), mask, C, Hs, Ws, Hd,  \
+                                          Wd, cams, cam_stride, mode, ch_per_cta, ch_per_stage, src_repeat,       \
+                                          tile_px);                                                               \
+  }
+    if (qpt <= 1) PF_LAUNCH_QUAD(1)
+    else PF_LAUNCH_QUAD(2)
+#undef PF_LAUNCH_QUAD
+    PF_CHECK_LAUNCH("resample_quad_kernel");
+    return PF_OK;
+  }
+  if (src_repeat != 1) {
+    set_error("pf_e2p/pf_p2e: src_repeat > 1 needs the staged quad path (output width %% 4 == 0, source plane <= 48 KB)");
+    return PF_ERR_UNSUPPORTED;
+  }
   // staged path: plane must fit twice (double buffer) in <= ~96 KB so two CTAs share an SM, <= 8 pixels/thread
   if (aligned && plane_bytes <= 48 * 1024 && dplane <= 8 * STG_THREADS && C >= 4) {
     int ch_per_stage = (int)((48 * 1024) / plane_bytes);
@@ -207,7 +378,7 @@ static int launch_resample(const void* src, void* dst, uint8_t* mask, int B, int
 
 template <bool P2E>
 static int dispatch_resample(const void* src, void* dst, uint8_t* mask, int dtype, int B, int C, int Hs, int Ws,
-                             int Hd, int Wd, const double* cams, int cam_stride, int mode, void* stream) {
+                             int Hd, int Wd, const double* cams, int cam_stride, int mode, int src_repeat, void* stream) {
   const char* name = P2E ? "pf_p2e" : "pf_e2p";
   PF_CHECK_ARG(src && dst && cams, "%s: null pointer", name);
   PF_CHECK_ARG(B > 0 && C > 0 && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0, "%s: empty shape", name);
@@ -215,14 +386,15 @@ static int dispatch_resample(const void* src, void* dst, uint8_t* mask, int dtyp
   PF_CHECK_ARG(cam_stride == 0 || cam_stride == 1, "%s: cam_stride must be 0 or 1", name);
   // reference: choose_mode() accepts 'bilinear'/'nearest' for tensors, ValueError otherwise (utils.py:5-15)
   PF_CHECK_ARG(mode == 0 || mode == 1, "%s: mode must be one of [bilinear, nearest]", name);
+  PF_CHECK_ARG(src_repeat >= 1 && B % src_repeat == 0, "%s: src_repeat=%d must divide the batch %d", name, src_repeat, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (dtype) {
     case PF_F32:
-      return launch_resample<float, P2E>(src, dst, mask, B, C, Hs, Ws, Hd, Wd, cams, cam_stride, mode, st);
+      return launch_resample<float, P2E>(src, dst, mask, B, C, Hs, Ws, Hd, Wd, cams, cam_stride, mode, src_repeat, st);
     case PF_F16:
-      return launch_resample<__half, P2E>(src, dst, mask, B, C, Hs, Ws, Hd, Wd, cams, cam_stride, mode, st);
+      return launch_resample<__half, P2E>(src, dst, mask, B, C, Hs, Ws, Hd, Wd, cams, cam_stride, mode, src_repeat, st);
     case PF_BF16:
-      return launch_resample<__nv_bfloat16, P2E>(src, dst, mask, B, C, Hs, Ws, Hd, Wd, cams, cam_stride, mode, st);
+      return launch_resample<__nv_bfloat16, P2E>(src, dst, mask, B, C, Hs, Ws, Hd, Wd, cams, cam_stride, mode, src_repeat, st);
   }
   set_error("%s: unknown dtype %d", name, dtype);
   return PF_ERR_INVALID;
@@ -232,10 +404,16 @@ static int dispatch_resample(const void* src, void* dst, uint8_t* mask, int dtyp
 
 extern "C" int pf_e2p(const void* src, void* dst, int dtype, int B, int C, int He, int We, int h, int w,
                       const double* cams, int cam_stride, int mode, void* stream) {
-  return pf::dispatch_resample<false>(src, dst, nullptr, dtype, B, C, He, We, h, w, cams, cam_stride, mode, stream);
+  return pf::dispatch_resample<false>(src, dst, nullptr, dtype, B, C, He, We, h, w, cams, cam_stride, mode, 1, stream);
+}
+
+extern "C" int pf_e2p_shared(const void* src, void* dst, int dtype, int B, int src_repeat, int C, int He, int We, int h,
+                             int w, const double* cams, int cam_stride, int mode, void* stream) {
+  return pf::dispatch_resample<false>(src, dst, nullptr, dtype, B, C, He, We, h, w, cams, cam_stride, mode, src_repeat,
+                                      stream);
 }
 
 extern "C" int pf_p2e(const void* src, void* dst, uint8_t* mask, int dtype, int B, int C, int hp, int wp, int He,
                       int We, const double* cams, int cam_stride, int mode, void* stream) {
-  return pf::dispatch_resample<true>(src, dst, mask, dtype, B, C, hp, wp, He, We, cams, cam_stride, mode, stream);
+  return pf::dispatch_resample<true>(src, dst, mask, dtype, B, C, hp, wp, He, We, cams, cam_stride, mode, 1, stream);
 }

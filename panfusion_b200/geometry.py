@@ -96,18 +96,27 @@ def _mode_code(mode) -> int:
     raise ValueError("mode must be one of [bilinear, bicubic, nearest]")
 
 
-def e2p(e_img: Tensor, fov_deg, u_deg, v_deg, out_hw, mode=None) -> Tensor:
-    """Equirect [B,C,He,We] -> perspective [B,C,h,w] (e2p.py:54-76)."""
+def e2p(e_img: Tensor, fov_deg, u_deg, v_deg, out_hw, mode=None, views_per_image: int = 1) -> Tensor:
+    """Equirect [B,C,He,We] -> perspective [B,C,h,w] (e2p.py:54-76).
+
+    views_per_image > 1 (extension): e_img is [B / views_per_image, C, He, We] and camera b looks at image
+    b // views_per_image — what the reference gets by expanding one panorama to its m views before the call
+    (PanFusion.py:33-37), without materialising the copies."""
     _lib.require_cuda(e_img)
-    b, c, he, we = e_img.shape
+    bs, c, he, we = e_img.shape
+    b = bs * int(views_per_image)
     h, w = int(out_hw[0]), int(out_hw[1])
     e_img = e_img.contiguous()
     cams, stride = camera_records("e2p", fov_deg, u_deg, v_deg, b, h, w, e_img.device)
     out = torch.empty((b, c, h, w), dtype=e_img.dtype, device=e_img.device)
-    _lib.check(_lib.lib().pf_e2p(
-        _lib.C.c_void_p(e_img.data_ptr()), _lib.C.c_void_p(out.data_ptr()), _lib.dtype_code(e_img.dtype),
-        b, c, he, we, h, w, _lib.C.c_void_p(cams.data_ptr()), stride, _mode_code(mode),
-        _lib.C.c_void_p(_lib.stream_ptr())))
+    args = (_lib.C.c_void_p(e_img.data_ptr()), _lib.C.c_void_p(out.data_ptr()), _lib.dtype_code(e_img.dtype))
+    tail = (c, he, we, h, w, _lib.C.c_void_p(cams.data_ptr()), stride, _mode_code(mode), _lib.C.c_void_p(_lib.stream_ptr()))
+    if views_per_image == 1:
+        _lib.check(_lib.lib().pf_e2p(*args, b, *tail))
+    else:
+        if not stride:
+            raise ValueError("views_per_image needs per-view cameras")
+        _lib.check(_lib.lib().pf_e2p_shared(*args, b, int(views_per_image), *tail))
     return out
 
 

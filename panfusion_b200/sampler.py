@@ -70,8 +70,8 @@ class PanFusionSampler:
         cams = {k: v.flatten(0, 1) for k, v in cameras.items()}
         m = len(cams["FoV"]) // bs
         pano_noise = torch.randn(bs, 1, 4, equi_h, equi_w, device=device, generator=generator)
-        rep = pano_noise.expand(-1, m, -1, -1, -1).flatten(0, 1).contiguous()
-        noise = geometry.e2p(rep, cams["FoV"], cams["theta"], cams["phi"], (pers_h, pers_w), mode="nearest")
+        noise = geometry.e2p(pano_noise[:, 0], cams["FoV"], cams["theta"], cams["phi"], (pers_h, pers_w), mode="nearest",
+                             views_per_image=m)  # = e2p of the panorama expanded to its m views (PanFusion.py:33-37)
         return pano_noise, noise.reshape(bs, m, *noise.shape[1:])
 
     # ---- PanFusion.py:114-123 / PanoGenerator.py:264-269 ------------------------------------------
@@ -229,8 +229,8 @@ class PanFusionSampler:
             cams = {k: v.flatten(0, 1) for k, v in cameras.items()}
             m = len(cams["FoV"])
             pano_noise = pano_noise.to(device)
-            rep = pano_noise.expand(-1, m, -1, -1, -1).flatten(0, 1).contiguous()
-            noise = geometry.e2p(rep, cams["FoV"], cams["theta"], cams["phi"], tuple(pers_hw), mode="nearest")[None]
+            noise = geometry.e2p(pano_noise[:, 0], cams["FoV"], cams["theta"], cams["phi"], tuple(pers_hw), mode="nearest",
+                                 views_per_image=m)[None]
         lat, pano = self.denoise(noise, pano_noise, prompt_embd.to(device), pano_prompt_embd.to(device), cameras,
                                  num_steps=num_steps, pers_layout_cond=pers_layout_cond,
                                  pano_layout_cond=pano_layout_cond)

@@ -38,9 +38,14 @@ def _err(got, ref):
     return d.max().item() / scale, d.mean().item() / scale
 
 
-def _check(name, got, ref, dtype):
+# the EPPA test compares the residual UPDATE alone (a few per cent of the activations' magnitude), so its relative error is
+# larger than that of whole-model outputs: measured fp16 7.4e-3 / 4.0e-4, bf16 5.1e-2 / 2.8e-3 -> gates at 2x
+UPDATE_LIMITS = {torch.float16: (1.5e-2, 1e-3), torch.bfloat16: (1e-1, 6e-3)}
+
+
+def _check(name, got, ref, dtype, limits=None):
     mx, mean = _err(got.float().cpu(), ref)
-    lim = LIMITS[dtype]
+    lim = (limits or LIMITS)[dtype]
     print(f"[parity] {name} {dtype}: max {mx:.3e} mean {mean:.3e} (of max|ref|) limits {lim}")
     assert mx <= lim[0] and mean <= lim[1], (name, mx, mean)
 
@@ -68,8 +73,8 @@ def test_warpattn_vs_reference_golden(cuda_device, dtype):
     torch.testing.assert_close(oq, torch.from_numpy(gold["equi_out"]), rtol=1e-5, atol=1e-5)
     gp, ge = mine.to(cuda_device)(px.to(cuda_device), ex.to(cuda_device), c4, compute_dtype=dtype)
     # the block is residual: compare the UPDATE it adds, which is what the kernels compute
-    _check("WarpAttn pers update", gp.float().cpu() - px, torch.from_numpy(gold["pers_out"]) - px, dtype)
-    _check("WarpAttn equi update", ge.float().cpu() - ex, torch.from_numpy(gold["equi_out"]) - ex, dtype)
+    _check("WarpAttn pers update", gp.float().cpu() - px, torch.from_numpy(gold["pers_out"]) - px, dtype, UPDATE_LIMITS)
+    _check("WarpAttn equi update", ge.float().cpu() - ex, torch.from_numpy(gold["equi_out"]) - ex, dtype, UPDATE_LIMITS)
 
 
 def _build_mine(cuda_device, config, dtype):

@@ -57,12 +57,12 @@ def test_three_steps_vs_oracle_and_graph_replay(cuda_device, dtype):
     for name, got, ref in (("latents", outs[True][0], rl), ("pano", outs[True][1], rp)):
         err = (got - ref).abs().max().item() / ref.abs().max().item()
         print(f"[parity] {n}-step sampler {name}: max err {err:.3e} of max|ref|")
-        assert err < 3e-2
+        assert err < 2e-3  # 2x the measured 9.2e-4 (fp16, 5 steps)
     # rotate_back (PanFusion.py:164)
     s = PanFusionSampler(mine, use_cuda_graph=False)
     _, gp_back = s.denoise(dev(lat), dev(pano), dev(prompt), dev(pano_prompt), cams, num_steps=n)
     ref_back = torch.roll(rp, int(-n * 90 / 360 * 32), dims=-1)
-    assert (gp_back.cpu() - ref_back).abs().max().item() / ref_back.abs().max().item() < 3e-2
+    assert (gp_back.cpu() - ref_back).abs().max().item() / ref_back.abs().max().item() < 2e-3
 
 
 def test_layout_conditioned_steps_vs_oracle_and_graph_replay(cuda_device):
@@ -102,7 +102,7 @@ def test_layout_conditioned_steps_vs_oracle_and_graph_replay(cuda_device):
     for name, got, ref in (("latents", outs[True][0], rl), ("pano", outs[True][1], rp)):
         err = (got - ref).abs().max().item() / ref.abs().max().item()
         print(f"[parity] {n}-step layout-conditioned sampler {name}: max err {err:.3e} of max|ref|")
-        assert err < 3e-2
+        assert err < 2e-3  # 2x the measured 9.2e-4 (fp16, 5 steps)
 
 
 def test_sampler_reuses_buffers_and_graphs_across_images(cuda_device):

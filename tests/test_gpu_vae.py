@@ -50,7 +50,8 @@ def _cmp(name, got, ref, dtype):
     scale = ref.abs().max().item()
     d = (got.float().cpu() - ref).abs()
     mx, mean = d.max().item() / scale, d.mean().item() / scale
-    lim = (1.5e-2, 2e-3) if dtype == torch.float16 else (8e-2, 1.2e-2)
+    # 2x the measured worst case (fp16 3.4e-3 / 2.8e-4, bf16 3.0e-2 / 2.2e-3 of max|ref|)
+    lim = (7e-3, 6e-4) if dtype == torch.float16 else (6e-2, 4.5e-3)
     print(f"[parity] {name} {dtype}: max {mx:.3e} mean {mean:.3e} (of max|ref|) limits {lim}")
     assert mx <= lim[0] and mean <= lim[1]
 
