@@ -279,6 +279,21 @@ int pf_eppa_tables(const double* cams_e2p, const double* cams_p2e, int V, int m,
 int pf_eppa_pe(const double* cams_e2p, int V, int ph, int pw, int eh, int ew, const float* freq_bands, int n_freqs,
                float* pers_pe, float* equi_pe, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * View-sharded step: device-initiated all-gather over NVLink peer mappings, capturable in a CUDA graph.
+ * The reference has no model parallelism (Lightning DDP over prompts, main.py:63); this is the exchange the view partition
+ * needs: models/pano/modules.py:44-48 lets every panorama query attend to the keys / values of ALL views, so each rank
+ * publishes the projected K|V of its local views before every EPPA block (and the eps outputs at the end of the step).
+ *   local         this rank's slice (slice_bytes, multiple of 16)
+ *   peer_data     DEVICE array [nranks] of pointers: every rank's receive buffer [nranks][slice_bytes] for this call site,
+ *                 mapped into this process (CUDA IPC / peer access); entry `rank` is the own buffer
+ *   peer_flags    DEVICE array [nranks] of pointers to every rank's nranks flag words (zero-initialised, uint32)
+ *   my_flags      == peer_flags[rank];  state: 2 zero-initialised uint32 of this rank (epoch, CTA counter)
+ * On return (stream order) the own receive buffer holds every rank's slice in rank order. One kernel: push to all peers,
+ * publish the epoch, wait for all peers; a peer that never arrives makes the kernel trap after ~2 s instead of hanging. */
+int pf_allgather_views(const void* local, long long slice_bytes, void* const* peer_data, unsigned int* const* peer_flags,
+                       unsigned int* my_flags, unsigned int* state, int rank, int nranks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,9 @@ class MultiViewBaseModel(nn.Module):
                 w.tables = tables
         self._branches = None
         self._par = None
+        # which set of all-gather receive buffers this forward uses (parallel.DeviceAllGather): consecutive steps must
+        # use different slots; the sampler sets it (one slot per captured graph, or the step parity when eager)
+        self.par_slot = 0
 
     def set_view_parallel(self, group=None, batch_shards=None, view_shards=None) -> None:
         """Shard the step over the ranks of `group` (parallel.ViewParallel): CFG halves first, then views."""
@@ -120,6 +123,7 @@ class MultiViewBaseModel(nn.Module):
             # keep this rank's CFG/batch elements and views; cameras of ALL views stay (EPPA bias needs them)
             b_full, m_full = latents.shape[:2]
             par.configure(b_full, m_full)
+            par.begin_step(self.par_slot)
             bsl, vsl = par.slices(b_full, m_full)
             latents, timestep, prompt_embd = latents[bsl, vsl], timestep[bsl, vsl], prompt_embd[bsl, vsl]
             pano_latent, pano_prompt_embd = pano_latent[bsl], pano_prompt_embd[bsl]

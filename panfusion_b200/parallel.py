@@ -12,6 +12,12 @@ queries attend to the keys/values of ALL views (models/pano/modules.py:44-48). L
 Collectives: (1) per EPPA block, ONE all-gather of the projected K|V of the local views inside the batch shard's
 view group (skipped when view_shards == 1, e.g. N = 2 = pure CFG split); (2) per forward, one all-gather of the tiny
 eps outputs over the world so every rank ends the step with identical full latents.
+
+Transport. Default: `DeviceAllGather` — receive buffers shared between the processes of the node through CUDA IPC
+(`torch` storage sharing), filled by the peers' `pf_allgather_views` kernels with plain stores over NVLink and
+synchronised with flag words in the same mappings. The collective is an ordinary kernel on the compute stream, so the
+whole step stays ONE CUDA graph. `PF_DEVICE_GATHER=0` selects NCCL (`torch.distributed.all_gather_into_tensor`), which is
+issued from the host between graph segments (`GraphSegments`).
 """
 from __future__ import annotations
 
@@ -20,6 +26,78 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 from torch import Tensor
+
+
+DEVICE_GATHER = __import__("os").environ.get("PF_DEVICE_GATHER", "1") != "0"
+
+
+class _Site:
+    __slots__ = ("recv", "ctrl", "peer_data", "peer_flags", "keep")
+
+
+class DeviceAllGather:
+    """All-gather inside `group` through IPC-mapped receive buffers and the `pf_allgather_views` kernel.
+
+    A call site is identified by `key` (slot, index of the collective inside the step, shape): its buffers are created on
+    first use — an eager, host-synchronising exchange of IPC handles, so the first step of every slot must run eagerly
+    (the sampler's warm-up step does) — and reused afterwards. `slot` separates the buffers of consecutive steps: a site
+    is rewritten only after every peer has passed at least one later collective of the SAME slot sequence (see
+    csrc/comm.cu), which the sampler guarantees by cycling through >= 2 slots."""
+
+    def __init__(self, group):
+        self.group = group
+        self.S = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.sites: dict = {}
+
+    def _create(self, key, x: Tensor) -> _Site:
+        import ctypes as C
+        S = self.S
+        site = _Site()
+        site.recv = torch.empty((S, *x.shape), dtype=x.dtype, device=x.device)
+        site.ctrl = torch.zeros(64, dtype=torch.int32, device=x.device)  # [0:S) flags, [S], [S+1] epoch / CTA counter
+        torch.cuda.synchronize()
+        mine = [t.untyped_storage()._share_cuda_() for t in (site.recv, site.ctrl)]
+        offs = [site.recv.storage_offset() * site.recv.element_size(), site.ctrl.storage_offset() * 4]
+        everyone = [None] * S
+        dist.all_gather_object(everyone, (mine, offs), group=self.group)
+        data_ptrs, flag_ptrs, site.keep = [], [], []
+        for r, (handles, off) in enumerate(everyone):
+            if r == self.rank:
+                data_ptrs.append(site.recv.data_ptr())
+                flag_ptrs.append(site.ctrl.data_ptr())
+                continue
+            st = [torch.UntypedStorage._new_shared_cuda(*h) for h in handles]
+            site.keep.append(st)  # the mappings live as long as the site
+            data_ptrs.append(st[0].data_ptr() + off[0])
+            flag_ptrs.append(st[1].data_ptr() + off[1])
+        site.peer_data = torch.tensor(data_ptrs, dtype=torch.int64, device=x.device)
+        site.peer_flags = torch.tensor(flag_ptrs, dtype=torch.int64, device=x.device)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)  # every rank's flag words are zeroed and mapped before anyone pushes
+        self.sites[key] = site
+        return site
+
+    def all_gather(self, key, x: Tensor) -> Tensor:
+        """x contiguous, identical shape on every rank -> [S, *x.shape] (rank order), valid in stream order."""
+        import ctypes as C
+        from . import _lib, ops
+        assert x.is_contiguous()
+        key = (key, tuple(x.shape), x.dtype)
+        site = self.sites.get(key)
+        if site is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("DeviceAllGather: a new call site cannot be created while a CUDA graph is being captured "
+                                   "(run one eager step first)")
+            site = self._create(key, x)
+        nbytes = x.numel() * x.element_size()
+        ctrl = site.ctrl.data_ptr()
+        ops._count(1)
+        _lib.check(_lib.lib().pf_allgather_views(
+            C.c_void_p(x.data_ptr()), C.c_longlong(nbytes), C.c_void_p(site.peer_data.data_ptr()),
+            C.c_void_p(site.peer_flags.data_ptr()), C.c_void_p(ctrl), C.c_void_p(ctrl + 4 * self.S), self.rank, self.S,
+            C.c_void_p(_lib.stream_ptr())))
+        return site.recv
 
 
 def pick_layout(world: int, b: int, m: int) -> tuple[int, int]:
@@ -84,7 +162,19 @@ class ViewParallel:
         self.rank = dist.get_rank(self.group)
         self.batch_shards, self.view_shards = batch_shards, view_shards
         self._view_groups = None
-        self.segments: Optional[GraphSegments] = None  # set by the sampler while it captures a step
+        self.segments: Optional[GraphSegments] = None  # set by the sampler while it captures a step (NCCL transport)
+        self.device_gather = DEVICE_GATHER
+        self._dev_view: Optional[DeviceAllGather] = None
+        self._dev_world: Optional[DeviceAllGather] = None
+        self._slot, self._site = 0, 0
+
+    def begin_step(self, slot: int = 0) -> None:
+        """Called at the start of every forward: `slot` selects the set of receive buffers (see DeviceAllGather)."""
+        self._slot, self._site = int(slot), 0
+
+    def _next_key(self):
+        self._site += 1
+        return (self._slot, self._site)
 
     def _run(self, fn) -> None:
         if self.segments is not None:
@@ -118,9 +208,14 @@ class ViewParallel:
         if self.view_shards == 1:
             return x
         bl, L, C = x.shape
-        out = torch.empty((self.view_shards * bl, L, C), dtype=x.dtype, device=x.device)  # concat along dim 0
-        xc, grp = x.contiguous(), self.view_group
-        self._run(lambda: dist.all_gather_into_tensor(out, xc, group=grp))
+        if self.device_gather:
+            if self._dev_view is None:
+                self._dev_view = DeviceAllGather(self.view_group)
+            out = self._dev_view.all_gather(self._next_key(), x.contiguous())
+        else:
+            out = torch.empty((self.view_shards * bl, L, C), dtype=x.dtype, device=x.device)  # concat along dim 0
+            xc, grp = x.contiguous(), self.view_group
+            self._run(lambda: dist.all_gather_into_tensor(out, xc, group=grp))
         out = out.reshape(self.view_shards, bl, L, C)
         if bl == 1:
             return out.reshape(1, self.view_shards * L, C)
@@ -129,20 +224,28 @@ class ViewParallel:
     def gather_outputs(self, sample_loc: Optional[Tensor], pano_loc: Tensor, b: int, m: int):
         """sample_loc [b_loc, m_loc, ...], pano_loc [b_loc, 1, ...] -> full [b, m, ...], [b, 1, ...] on every rank."""
         bl, ml = b // self.batch_shards, m // self.view_shards
-        pano_all = torch.empty((self.world * pano_loc.shape[0], *pano_loc.shape[1:]), dtype=pano_loc.dtype,
-                               device=pano_loc.device)
         pc, grp = pano_loc.contiguous(), self.group
         s_all, sc = None, None
-        if sample_loc is not None:
-            sc = sample_loc.contiguous()
-            s_all = torch.empty((self.world * sc.shape[0], *sc.shape[1:]), dtype=sc.dtype, device=sc.device)
+        if self.device_gather:
+            if self._dev_world is None:
+                self._dev_world = DeviceAllGather(self.group)
+            pano_all = self._dev_world.all_gather(self._next_key(), pc)
+            if sample_loc is not None:
+                sc = sample_loc.contiguous()
+                s_all = self._dev_world.all_gather(self._next_key(), sc)
+        else:
+            pano_all = torch.empty((self.world * pano_loc.shape[0], *pano_loc.shape[1:]), dtype=pano_loc.dtype,
+                                   device=pano_loc.device)
+            if sample_loc is not None:
+                sc = sample_loc.contiguous()
+                s_all = torch.empty((self.world * sc.shape[0], *sc.shape[1:]), dtype=sc.dtype, device=sc.device)
 
-        def both():
-            dist.all_gather_into_tensor(pano_all, pc, group=grp)
-            if s_all is not None:
-                dist.all_gather_into_tensor(s_all, sc, group=grp)
+            def both():
+                dist.all_gather_into_tensor(pano_all, pc, group=grp)
+                if s_all is not None:
+                    dist.all_gather_into_tensor(s_all, sc, group=grp)
 
-        self._run(both)
+            self._run(both)
         pano = pano_all.reshape(self.batch_shards, self.view_shards, *pano_loc.shape)[:, 0].reshape(b, *pano_loc.shape[1:])
         sample = None
         if sample_loc is not None:

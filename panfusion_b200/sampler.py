@@ -239,7 +239,10 @@ class PanFusionSampler:
         return images, pano_img
 
     def _run_step(self, st, cameras):
+        par = getattr(self.mv_base_model, "_par", None)
+        self._steps_run = getattr(self, "_steps_run", 0) + 1
         if not self.use_cuda_graph:
+            self.mv_base_model.par_slot = self._steps_run % 2  # consecutive steps: different receive buffers
             l0 = ops.LAUNCHES
             self._step_body(st, cameras)
             self.launches_per_step = ops.LAUNCHES - l0
@@ -248,20 +251,28 @@ class PanFusionSampler:
                tuple(cameras["FoV"].reshape(-1).tolist()), tuple(st["latents"].shape), tuple(st["pano"].shape),
                st["latents"].data_ptr(), st["pano"].data_ptr(), st["prompt"].data_ptr(),
                st["pano_cond"].data_ptr() if "pano_cond" in st else 0)
+        if par is not None and not (self.rot_diff % 360):
+            key += (self._steps_run % 2,)  # a single rotation phase: still alternate between two graphs / buffer sets
         entry = self._graphs.get(key)
         if entry is None:
             # eager warm-up builds the camera tables / packs weights / sets kernel attributes, then capture
             snap = {k: st[k].clone() for k in ("latents", "pano")}
+            self._slot_seq = getattr(self, "_slot_seq", 1) + 1
+            self.mv_base_model.par_slot = self._slot_seq  # this graph's own all-gather receive buffers
             self._step_body(st, cameras)
             torch.cuda.synchronize()
+            if par is not None and getattr(par, "device_gather", False) and hasattr(par, "group"):
+                # every rank has CONSUMED what the warm-up step gathered before the same receive buffers are used again
+                import torch.distributed as dist
+                dist.barrier(group=par.group)
             st["latents"].copy_(snap["latents"])
             st["pano"].copy_(snap["pano"])
             if self._pool is None:
                 self._pool = torch.cuda.graph_pool_handle()
-            par = getattr(self.mv_base_model, "_par", None)
             l0 = ops.LAUNCHES
-            if par is not None:
-                # sharded step: NCCL collectives stay OUTSIDE the graphs (parallel.GraphSegments)
+            if par is not None and not par.device_gather:
+                # sharded step over NCCL: the collectives stay OUTSIDE the graphs (parallel.GraphSegments); the default
+                # device-side all-gather (pf_allgather_views) is an ordinary kernel and is captured like everything else
                 from .parallel import GraphSegments
                 g = GraphSegments(self._pool)
                 par.segments = g

@@ -65,14 +65,15 @@ def main():
             model = build(dev, parallel)
             s = PanFusionSampler(model, use_cuda_graph=graph)
             log("denoise")
-            outs.append(s.denoise(lat, pano, prompt, pano_prompt, cams, num_steps=5, rotate_back=False))
+            outs.append(s.denoise(lat, pano, prompt, pano_prompt, cams, num_steps=9, rotate_back=False))
             torch.cuda.synchronize()
             log("done, barrier")
             dist.barrier()
         d_lat = (outs[0][0] - outs[1][0]).abs().max().item()
         d_pano = (outs[0][1] - outs[1][1]).abs().max().item()
         scale = outs[0][0].abs().max().item()
-        good = d_lat <= 2e-3 * scale and d_pano <= 2e-3 * scale
+        tol = float(os.environ.get("MGPU_TOL", "0"))  # the sharded step is bit-identical to the single-GPU one
+        good = d_lat <= tol * scale and d_pano <= tol * scale
         ok = ok and good
         if rank == 0:
             print(f"[mgpu] world={world} graph={graph}: |sharded - single| latents {d_lat:.3e} pano {d_pano:.3e} "

@@ -29,6 +29,7 @@ class EmulatedParallel(ViewParallel):
         self.world, self.rank = batch_shards * view_shards, 0
         self.segments = None
         self.whole_graph = whole_graph
+        self.device_gather = whole_graph  # True: the stand-in collectives are captured like pf_allgather_views is
         self.bs = self.vs = 0
 
     def _run(self, fn):

@@ -18,6 +18,7 @@ class ReplayParallel(ViewParallel):
         self.world, self.rank = batch_shards * view_shards, bs * view_shards + vs
         self.bs, self.vs = bs, vs
         self.segments = None
+        self.device_gather = False
         self.recorded, self.block = recorded, 0
         self.worst_local = 0.0
         self.outputs = None

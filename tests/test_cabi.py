@@ -93,3 +93,20 @@ def test_camera_table_dedup():
     cams["theta"] = torch.tensor([0.0, 180.0, 90.0, 270.0])
     key, groups = CameraTables.dedup(CameraTables.camera_key(cams), 2)
     assert groups == 2 and len(key[0]) == 4
+
+
+def test_row_stats_slots_ignore_tile_requests():
+    """A fused-LayerNorm PRODUCER's slot layout is a function of N alone (never of a tile-width request or of tuning), and the
+    query gives the same answer before and after the caller has filled in row_stats_out."""
+    import ctypes as C
+    from panfusion_b200 import _lib
+    lib = _lib.lib()
+    for n, want in ((320, 4), (640, 8), (1280, 16), (128, 2), (64, 2)):
+        seen = set()
+        for req in (0, 64, 128, 64 | (2 << 16), 256 | (1 << 16)):
+            a = _lib.GemmArgs()
+            a.N, a.M, a.Kc, a.num_taps, a.block_n = n, 512, n, 1, req
+            seen.add(lib.pf_gemm_row_stats_slots(C.byref(a)))
+            a.row_stats_out = 1
+            seen.add(lib.pf_gemm_row_stats_slots(C.byref(a)))
+        assert seen == {want}, (n, seen)
