@@ -57,6 +57,17 @@ int pf_e2p(const void* src, void* dst, int dtype, int B, int C, int He, int We, 
 int pf_e2p_shared(const void* src, void* dst, int dtype, int B, int src_repeat, int C, int He, int We, int h, int w,
                   const double* cams, int cam_stride, int mode, void* stream);
 
+/* py360convert.e2p (external/py360convert/e2p.py:6-43, utils.py:104-132,231-243): the dataset's pixel-space convention
+ * (utils/pano.py:160-161 `Equirectangular.to_perspective`, dataset/PanoDataset.py:138) — channels-last src[H, W, C] (uint8 when
+ * is_u8, else fp32) -> dst[num_cams, h, w, C]; half-pixel centres (uv2coor), longitude wrap-around, pole rows padded with the
+ * first / last row rolled by W/2, scipy 'wrap' boundaries, float64 grid math, integers rounded half up.
+ * Camera record: PF_CAM360_DOUBLES doubles = Rx, Ry, Ri (row-major; rotation_matrix(v,[1,0,0]), rotation_matrix(-yaw,[0,1,0]),
+ * rotation_matrix(in_rot, z Rx Ry)), tan(h_fov/2), tan(v_fov/2). mode: 0 bilinear, 1 nearest; anything else is
+ * PF_ERR_UNSUPPORTED like the reference's NotImplementedError('unknown mode'). */
+#define PF_CAM360_DOUBLES 29
+int pf_e2p_py360(const void* src, void* dst, int is_u8, int H, int W, int C, int h, int w, const double* cams,
+                 int num_cams, int mode, void* stream);
+
 /* p2e(p_img[B,C,hp,wp]) -> equi[B,C,He,We] (already multiplied by mask), mask[B,1,He,We] uint8 (may be NULL)
  * (p2e.py:52-77; grid math p2e.py:9-49) */
 int pf_p2e(const void* src, void* dst, uint8_t* mask, int dtype, int B, int C, int hp, int wp, int He, int We,

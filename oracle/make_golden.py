@@ -4,6 +4,7 @@ check the oracle restatement against them. Runs only where /root/reference is mo
     python -m oracle.make_golden [--full]     # --full adds the SD-2-size C1 step (minutes on 8 cores)
     python -m oracle.make_golden --only c2    # BASELINE configs[1]: SD-2 widths, 8 views, CFG pair (b = 2)
     python -m oracle.make_golden --only c4geo # get_masks at config 4's real level size (32x32 views, 64x128 pano)
+    python -m oracle.make_golden --only py360 # external/py360convert e2p (dataset convention) on seeded images
 
 Each fixture stores the seeded inputs' identifying parameters and the reference outputs; tests regenerate the
 inputs from the seeds (same torch build on both boxes) and compare.
@@ -83,10 +84,39 @@ def golden_c4_geometry(ref):
     return err
 
 
+PY360_CASES = [  # (fov (h, v), yaw u, pitch v, out_hw, in_rot, mode): poles, the +-180 seam, non-square FoV, roll
+    ((90, 90), 30.0, 20.0, (48, 48), 0.0, "bilinear"), ((90, 90), 180.0, -85.0, (40, 56), 10.0, "bilinear"),
+    ((70, 100), -170.0, 88.0, (33, 21), 0.0, "nearest"), ((90, 90), 0.0, 0.0, (64, 64), 0.0, "bilinear"),
+    ((90, 90), -179.5, 0.0, (32, 32), 0.0, "nearest")]
+
+
+def py360_images():
+    rng = np.random.default_rng(0)
+    return rng.integers(0, 256, (64, 128, 3)).astype(np.uint8), rng.random((32, 64, 2)).astype(np.float32)
+
+
+def golden_py360():
+    """external/py360convert/e2p.py executed by path (it imports cleanly: numpy + scipy) on seeded images."""
+    import importlib
+    from . import py360 as op
+    if str(ref_loader.REF) not in sys.path:
+        sys.path.insert(0, str(ref_loader.REF))
+    ref360 = importlib.import_module("external.py360convert")
+    out, worst = {}, 0.0
+    for k, (fov, u, v, hw, rot, mode) in enumerate(PY360_CASES):
+        for tag, im in zip(("u8", "f32"), py360_images()):
+            r = ref360.e2p(im, fov, u, v, hw, in_rot_deg=rot, mode=mode)
+            out[f"case{k}_{tag}"] = r
+            worst = max(worst, float(np.abs(r.astype(np.float64) - op.e2p(im, fov, u, v, hw, rot, mode).astype(np.float64)).max()))
+    print(f"  py360convert.e2p: max |oracle - reference| = {worst:.3e}")
+    np.savez_compressed(OUT / "py360_e2p.npz", **out)
+    return worst
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
-    ap.add_argument("--only", choices=["c2", "c4geo"], help="mint just one of the large fixtures")
+    ap.add_argument("--only", choices=["c2", "c4geo", "py360"], help="mint just one of the separately kept fixtures")
     args = ap.parse_args()
     ref = ref_loader.load()
     OUT.mkdir(parents=True, exist_ok=True)
@@ -96,6 +126,8 @@ def main():
         return 0 if golden_c2(ref) < 1e-4 else 1
     if args.only == "c4geo":
         return 0 if golden_c4_geometry(ref) < 1e-5 else 1
+    if args.only == "py360":
+        return 0 if golden_py360() == 0.0 else 1
 
     # 1. resampling (e2p.py:54-76, p2e.py:52-77)
     g = torch.Generator().manual_seed(0)

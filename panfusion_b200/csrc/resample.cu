@@ -402,6 +402,107 @@ static int dispatch_resample(const void* src, void* dst, uint8_t* mask, int dtyp
 
 }  // namespace pf
 
+// ---------------------------------------------------------------------------------------------------
+// py360convert convention (external/py360convert/e2p.py:6-43, utils.py:104-132): the pixel-space equirect -> perspective
+// resampling of the dataset path (utils/pano.py:160-161, dataset/PanoDataset.py:138). Channels-last images [H, W, C],
+// half-pixel centres, longitude wrap-around, pole rows padded with the first / last row rolled by W/2, scipy's legacy
+// 'wrap' boundary (period n - 1), float64 grid math, integer images rounded half up. thread <-> output pixel.
+// ---------------------------------------------------------------------------------------------------
+namespace pf {
+
+__device__ __forceinline__ double py360_wrap(double c, int n) {
+  const double sz = double(n - 1);
+  if (c < 0.0) c += sz * double((long long)(-c / sz) + 1);
+  else if (c > sz) c -= sz * double((long long)(c / sz));
+  return c;
+}
+
+// row r of the padded image [H + 2][W]: r < H plain, r == H the last row rolled by W/2, r == H+1 the first row rolled
+__device__ __forceinline__ long long py360_src_index(int r, int x, int H, int W) {
+  if (r < H) return (long long)r * W + x;
+  const int xr = (x - W / 2 + W) % W;  // np.roll(row, W // 2)[x] == row[(x - W//2) mod W]
+  return (long long)(r == H ? H - 1 : 0) * W + xr;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+e2p_py360_kernel(const T* __restrict__ src, T* __restrict__ dst, int H, int W, int C, int h, int w,
+                 const double* __restrict__ cams, int nearest) {
+  const int cam_i = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= h * w) return;
+  const int i = pix / w, j = pix - i * w;
+  const double* cam = cams + (size_t)cam_i * PF_CAM360_DOUBLES;
+  // xyzpers: float32 linspace grids, z = 1, then three float64 rotations applied to the ROW vector
+  double v[3] = {double(float(np_linspace(-cam[27], cam[27], w, j))), -double(float(np_linspace(-cam[28], cam[28], h, i))), 1.0};
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double* R = cam + 9 * r;
+    double o[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      o[k] = __dadd_rn(__dadd_rn(__dmul_rn(v[0], R[k]), __dmul_rn(v[1], R[3 + k])), __dmul_rn(v[2], R[6 + k]));
+    v[0] = o[0]; v[1] = o[1]; v[2] = o[2];
+  }
+  const double uu = atan2(v[0], v[2]);
+  const double vv = atan2(v[1], sqrt(v[0] * v[0] + v[2] * v[2]));
+  const double cx = (uu / (2.0 * M_PI) + 0.5) * double(W) - 0.5;
+  const double cy = (-vv / M_PI + 0.5) * double(H) - 0.5;
+  const int HP = H + 2;
+  const double y = py360_wrap(cy, HP), x = py360_wrap(cx, W);
+  T* out = dst + ((size_t)cam_i * h * w + pix) * C;
+  if (nearest) {
+    int yi = int(floor(y + 0.5)), xi = int(floor(x + 0.5));
+    if (yi > HP - 1) yi -= HP - 1;
+    if (xi > W - 1) xi -= W - 1;
+    const T* sp = src + py360_src_index(yi, xi, H, W) * C;
+    for (int c = 0; c < C; ++c) out[c] = sp[c];
+    return;
+  }
+  const int y0 = int(floor(y)), x0 = int(floor(x));
+  const double ty = y - double(y0), tx = x - double(x0);
+  int y1 = y0 + 1, x1 = x0 + 1;
+  if (y1 > HP - 1) y1 -= HP - 1;
+  if (x1 > W - 1) x1 -= W - 1;
+  const T* p00 = src + py360_src_index(y0, x0, H, W) * C;
+  const T* p01 = src + py360_src_index(y0, x1, H, W) * C;
+  const T* p10 = src + py360_src_index(y1, x0, H, W) * C;
+  const T* p11 = src + py360_src_index(y1, x1, H, W) * C;
+  const double w00 = (1.0 - ty) * (1.0 - tx), w01 = (1.0 - ty) * tx, w10 = ty * (1.0 - tx), w11 = ty * tx;
+  for (int c = 0; c < C; ++c) {
+    const double val = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(double(p00[c]), w00), __dmul_rn(double(p01[c]), w01)),
+                                           __dmul_rn(double(p10[c]), w10)), __dmul_rn(double(p11[c]), w11));
+    if constexpr (sizeof(T) == 1) {
+      const double r = floor(val + 0.5);
+      out[c] = T(r < 0.0 ? 0.0 : (r > 255.0 ? 255.0 : r));
+    } else {
+      out[c] = T(val);
+    }
+  }
+}
+
+}  // namespace pf
+
+extern "C" int pf_e2p_py360(const void* src, void* dst, int is_u8, int H, int W, int C, int h, int w, const double* cams,
+                            int num_cams, int mode, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(src && dst && cams, "pf_e2p_py360: null pointer");
+  PF_CHECK_ARG(H > 1 && W > 1 && C > 0 && h > 0 && w > 0 && num_cams > 0 && num_cams <= 65535, "pf_e2p_py360: bad shape");
+  // py360convert raises NotImplementedError('unknown mode') for anything but bilinear / nearest (e2p.py:21-26)
+  if (mode != 0 && mode != 1) {
+    set_error("pf_e2p_py360: unknown mode");
+    return PF_ERR_UNSUPPORTED;
+  }
+  dim3 grid((h * w + 255) / 256, num_cams);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_u8)
+    e2p_py360_kernel<uint8_t><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), H, W, C, h, w, cams, mode);
+  else
+    e2p_py360_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), H, W, C, h, w, cams, mode);
+  PF_CHECK_LAUNCH("e2p_py360_kernel");
+  return PF_OK;
+}
+
 extern "C" int pf_e2p(const void* src, void* dst, int dtype, int B, int C, int He, int We, int h, int w,
                       const double* cams, int cam_stride, int mode, void* stream) {
   return pf::dispatch_resample<false>(src, dst, nullptr, dtype, B, C, He, We, h, w, cams, cam_stride, mode, 1, stream);

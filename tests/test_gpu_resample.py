@@ -97,3 +97,52 @@ def test_bad_mode(cuda_device):
     from panfusion_b200 import geometry as pg
     with pytest.raises(ValueError):
         pg.e2p(torch.zeros(1, 1, 8, 16, device=cuda_device), 90, 0, 0, (4, 4), mode="bicubic")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_e2p_views_per_image_equals_expanded_source(cuda_device, dtype):
+    """pf_e2p_shared: m cameras per panorama == e2p of the panorama expanded to its m views (PanFusion.py:33-37),
+    bit for bit, for the staged quad path (feature-map shape) and a tiled large output plane."""
+    from panfusion_b200 import geometry as pg
+    for (bs, m, C, He, We, h, w) in ((2, 8, 320, 64, 128, 64, 64), (1, 3, 5, 32, 64, 96, 96)):
+        x = torch.randn(bs, C, He, We, generator=torch.Generator().manual_seed(6)).to(dtype).to(cuda_device)
+        fov, theta, phi = _cams(bs * m)
+        for mode in ("bilinear", "nearest"):
+            a = pg.e2p(x, fov, theta, phi, (h, w), mode=mode, views_per_image=m)
+            b = pg.e2p(x.repeat_interleave(m, 0), fov, theta, phi, (h, w), mode=mode)
+            assert a.shape == (bs * m, C, h, w) and torch.equal(a, b)
+    with pytest.raises(ValueError):
+        pg.e2p(x, 90, 0, 0, (8, 8), views_per_image=3)
+
+
+def test_py360convert_e2p_vs_reference_golden(cuda_device):
+    """pf_e2p_py360 (dataset-path convention, external/py360convert/e2p.py:6-43) against the golden minted by executing the
+    reference file: uint8 within one level on < 1e-4 of the pixels (float64 atan2 / tan of the device vs. the host libm
+    can move a value across a rounding boundary), fp32 images to 1e-6; `nearest` picks the same source pixel."""
+    from pathlib import Path
+    from oracle.make_golden import PY360_CASES, py360_images
+    from panfusion_b200 import py360
+    gold = np.load(Path(__file__).parent / "golden" / "py360_e2p.npz")
+    for k, (fov, u, v, hw, rot, mode) in enumerate(PY360_CASES):
+        for tag, im in zip(("u8", "f32"), py360_images()):
+            ref = gold[f"case{k}_{tag}"]
+            got = py360.e2p(im, fov, u, v, hw, in_rot_deg=rot, mode=mode)                 # numpy in -> numpy out
+            assert isinstance(got, np.ndarray) and got.shape == ref.shape and got.dtype == ref.dtype
+            d = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+            if tag == "u8" or mode == "nearest":
+                lim = 1 if mode == "bilinear" else 255
+                assert d.max() <= lim and (d > 0).mean() < 1e-4, (k, tag, d.max(), (d > 0).mean())
+            else:
+                assert d.max() < 1e-6, (k, tag, d.max())
+    # all views of a panorama in one launch, CUDA tensor in -> CUDA tensor out, 2-D image
+    im = py360_images()[0]
+    t = torch.from_numpy(im).to(cuda_device)
+    yaws, pitches = [0.0, 45.0, 200.0, -170.0], [0.0, 30.0, -60.0, 85.0]
+    multi = py360.e2p_views(t, (90, 90), yaws, pitches, (32, 32))
+    assert multi.is_cuda and multi.shape == (4, 32, 32, 3)
+    for i in range(4):
+        assert torch.equal(multi[i], py360.e2p(t, (90, 90), yaws[i], pitches[i], (32, 32)))
+    g2 = py360.e2p(im[..., 0], (90, 90), 30.0, 20.0, (48, 48))
+    assert g2.shape == (48, 48) and np.abs(g2.astype(int) - gold["case0_u8"][..., 0].astype(int)).max() <= 1
+    with pytest.raises(NotImplementedError):
+        py360.e2p(im, (90, 90), 0, 0, (4, 4), mode="bicubic")

@@ -175,3 +175,25 @@ def test_oracle_vae_tail_first_party_semantics():
     x = torch.tensor([[[[-1.0, 1.0, 0.0, -7.0, 7.0, 1 / 255]]]])  # 0.0 -> 127.5 -> 128 (half-to-even, torch.round)
     assert ov.tensor_to_image(x).tolist() == [[[[0], [255], [128], [0], [255], [128]]]]
     assert sum(p.numel() for p in ov.build_vae().parameters()) == 49490199  # the SD VAE decoder (+ post_quant_conv)
+
+
+def test_py360convert_e2p_matches_reference_golden_and_scipy():
+    """Dataset-path convention (external/py360convert/e2p.py:6-43): the restatement against the golden minted from the
+    reference file, and its hand-written 'wrap' interpolation against scipy.ndimage.map_coordinates itself."""
+    from scipy.ndimage import map_coordinates
+    from oracle import py360 as op
+    from oracle.make_golden import PY360_CASES, py360_images
+    gold = np.load(GOLD / "py360_e2p.npz")
+    for k, (fov, u, v, hw, rot, mode) in enumerate(PY360_CASES):
+        for tag, im in zip(("u8", "f32"), py360_images()):
+            np.testing.assert_array_equal(op.e2p(im, fov, u, v, hw, rot, mode), gold[f"case{k}_{tag}"])
+    rng = np.random.default_rng(3)
+    img = rng.random((9, 13))
+    cy, cx = rng.uniform(-20, 30, 5000), rng.uniform(-30, 40, 5000)
+    cy[:40], cx[:40] = rng.integers(-9, 18, 40), rng.integers(-13, 26, 40)
+    padded = np.concatenate([img, np.roll(img[[-1]], 13 // 2, 1), np.roll(img[[0]], 13 // 2, 1)], 0)
+    for order in (0, 1):
+        ref = map_coordinates(padded, [cy, cx], order=order, mode="wrap")
+        np.testing.assert_array_equal(op.sample_equirec(img, cx, cy, order), ref)
+    with pytest.raises(NotImplementedError):
+        op.e2p(img, (90, 90), 0, 0, (4, 4), mode="bicubic")
