@@ -264,6 +264,13 @@ int pf_tensor_to_image(const float* x, unsigned char* out, long long n, int C, i
 /* diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0) (MVGenModel.py:55,59): t fp32 [n] -> [n, dim] */
 int pf_timestep_embed(const float* t, void* out, int dtype, int n, int dim, void* stream);
 
+/* CLIP text embeddings (transformers CLIPTextEmbeddings [3P] behind PanoGenerator.encode_text, models/pano/PanoGenerator.py:
+ * 197-211): out[t, :] = tok_emb[ids[t], :] + pos_emb[t % L, :] (fp32 tables -> 16-bit tokens) and row_stats[t] = (sum, sum of
+ * squares, 0, 0) of the stored row — the two-slot statistics the first encoder layer's fused LayerNorm consumes
+ * (pf_gemm_args.ln_stats). ids int64 [T]; an id outside [0, vocab) traps (torch raises IndexError). */
+int pf_embed_tokens(const long long* ids, const float* tok_emb, const float* pos_emb, void* out, int dtype,
+                    float* row_stats, int T, int L, int C, int vocab, void* stream);
+
 /* Classifier-free-guidance combine + DDIM update (+ roll of the result by `roll` columns):
  *   e = eps[0:count] + guidance * (eps[count:2count] - eps[0:count])        (PanoGenerator.py:253-262)
  *   out[.., (col+roll) % W] = sqrt(a_prev) * (x - sqrt(1-a_t) e) / sqrt(a_t) + sqrt(1-a_prev) e   (DDIM, eta 0)

@@ -405,6 +405,57 @@ extern "C" int pf_tensor_to_image(const float* x, unsigned char* out, long long 
   return PF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// CLIP text embeddings (transformers CLIPTextEmbeddings [3P], called through PanoGenerator.encode_text,
+// models/pano/PanoGenerator.py:197-211): x[t, :] = token_embedding[ids[t], :] + position_embedding[t % L, :], plus the
+// per-row (sum, sum of squares) the first layer's fused LayerNorm consumes (two slots per row, the second zero).
+// One warp per token.
+// ------------------------------------------------------------------------------------------------
+namespace pf {
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+embed_tokens_kernel(const long long* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos,
+                    uint16_t* __restrict__ out, float* __restrict__ stats, int T, int L, int C, int vocab) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= T) return;
+  long long id = ids[t];
+  if (id < 0 || id >= vocab) __trap();  // torch.nn.Embedding raises an IndexError for such ids
+  const float* tr = tok + (size_t)id * C;
+  const float* pr = pos + (size_t)(t % L) * C;
+  float s = 0.f, q = 0.f;
+  for (int c = lane * 2; c < C; c += 64) {
+    const float a = __ldg(tr + c) + __ldg(pr + c), b = __ldg(tr + c + 1) + __ldg(pr + c + 1);
+    const uint32_t w = pack2<BF16>(a, b);
+    const float2 r = unpack2<BF16>(w);  // statistics of the STORED (16-bit) row, like a LayerNorm kernel reading it would see
+    s += r.x + r.y;
+    q = fmaf(r.x, r.x, fmaf(r.y, r.y, q));
+    *reinterpret_cast<uint32_t*>(out + (size_t)t * C + c) = w;
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) {
+    reinterpret_cast<float4*>(stats)[t] = make_float4(s, q, 0.f, 0.f);
+  }
+}
+}  // namespace pf
+
+extern "C" int pf_embed_tokens(const long long* ids, const float* tok_emb, const float* pos_emb, void* out, int dtype,
+                               float* row_stats, int T, int L, int C, int vocab, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(ids && tok_emb && pos_emb && out && row_stats, "pf_embed_tokens: null pointer");
+  PF_CHECK_ARG(dtype == PF_BF16 || dtype == PF_F16, "pf_embed_tokens: 16-bit output required");
+  PF_CHECK_ARG(T > 0 && L > 0 && C > 0 && C % 2 == 0 && vocab > 0, "pf_embed_tokens: bad shape T=%d L=%d C=%d", T, L, C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = (T + 7) / 8;
+  if (dtype == PF_BF16)
+    embed_tokens_kernel<true><<<blocks, 256, 0, st>>>(ids, tok_emb, pos_emb, static_cast<uint16_t*>(out), row_stats, T, L, C, vocab);
+  else
+    embed_tokens_kernel<false><<<blocks, 256, 0, st>>>(ids, tok_emb, pos_emb, static_cast<uint16_t*>(out), row_stats, T, L, C, vocab);
+  PF_CHECK_LAUNCH("embed_tokens_kernel");
+  return PF_OK;
+}
+
 extern "C" int pf_timestep_embed(const float* t, void* out, int dtype, int n, int dim, void* stream) {
   using namespace pf;
   PF_CHECK_ARG(t && out && n > 0 && dim > 0 && dim % 2 == 0, "pf_timestep_embed: bad arguments");

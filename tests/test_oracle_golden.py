@@ -197,3 +197,21 @@ def test_py360convert_e2p_matches_reference_golden_and_scipy():
         np.testing.assert_array_equal(op.sample_equirec(img, cx, cy, order), ref)
     with pytest.raises(NotImplementedError):
         op.e2p(img, (90, 90), 0, 0, (4, 4), mode="bicubic")
+
+
+def test_text_encoder_oracle_is_transformers_clip_and_causal():
+    """The text-encoder oracle EXECUTES transformers.CLIPTextModel (the reference's class, PanoGenerator.py:117-121) with the
+    SD-2 text-tower shape; check what the GPU tests rely on: seeded determinism, causality, final LayerNorm applied."""
+    from oracle import text_encoder as ot
+    import transformers
+    m = ot.build_text_encoder(ot.TINY_TEXT_CONFIG, seed=0)
+    assert isinstance(m, transformers.CLIPTextModel)
+    ids = ot.token_ids(2, vocab=1000, seed=1)
+    a = ot.encode_text(m, ids)
+    b = ot.encode_text(ot.build_text_encoder(ot.TINY_TEXT_CONFIG, seed=0), ids)
+    assert torch.equal(a, b) and a.shape == (2, 77, 128)
+    ids2 = ids.clone()
+    ids2[0, 30] = (ids2[0, 30] + 1) % 998
+    c = ot.encode_text(m, ids2)
+    assert torch.equal(c[0, :30], a[0, :30]) and not torch.equal(c[0, 30:], a[0, 30:])
+    assert ot.SD2_TEXT_CONFIG["num_hidden_layers"] == 23 and ot.SD2_TEXT_CONFIG["hidden_size"] // ot.SD2_TEXT_CONFIG["num_attention_heads"] == 64
