@@ -212,14 +212,17 @@ __global__ void __launch_bounds__(256) conv_prep_kernel(const PrepParams p) {
 //
 // grid = (chunks, G) with chunks * G <= GNP_MAX_CTAS, so that every CTA of the launch (and of one more such launch on
 // the other branch's stream) is co-resident: the kernel contains a per-image barrier. CTA (c, y) serves images
-// y, y + G, ... in turn. `chunks` depends on the image size ONLY, so the order of every floating-point sum — and with it
-// the result, bit for bit — is the same whatever the batch size (a view-sharded rank reproduces the single-GPU run). Phase 1: each CTA sums its band
+// y, y + G, ... in turn. The statistics are accumulated per SLAB — a fixed partition of the image into `slabs` pixel
+// ranges that depends on the image size ONLY — and the slabs are summed in slab order; how many slabs a CTA owns (few
+// CTAs per image for a big batch, many for a small one) does not enter any floating-point sum, so the result is the same,
+// bit for bit, whatever the batch size (a view-sharded rank reproduces the single-GPU run). Phase 1: each CTA sums its band
 // of source pixels per channel (two sources = the skip concatenation torch.cat([hidden, skip], 1), optionally also
 // written out raw), publishes per-group partials, and the LAST CTA of the image to arrive reduces them in a fixed
 // order (deterministic) into mean / rstd and releases the image's flag. Phase 2: after acquiring the flag each CTA
 // produces its share of the image's output positions — the source pixels are re-read from L2, not HBM.
 // sync[3n .. 3n+2] = {arrivals, flag, departures}: all zero on entry and restored to zero by the last CTA to leave.
 // ------------------------------------------------------------------------------------------------
+constexpr int GNP_MAX_SLABS = 32;  // statistics partition of one image (fixed by its size)
 constexpr int GNP_MAX_CTAS = 148;  // one CTA per SM; two such launches (2 CTAs of <= 512 threads per SM) stay co-resident
 
 __device__ __forceinline__ int ld_acquire_s32(const int* p) {
@@ -238,7 +241,8 @@ struct GnPrepParams {
   uint16_t* out;
   const float* gamma;
   const float* beta;
-  float* ws;            // [N][chunks][groups][2] partials, then [N][groups][2] mean/rstd at ws_mr
+  float* ws;            // [N][slabs][groups][2] partials, then [N][groups][2] mean/rstd at ws_mr
+  int slabs;            // statistics partition of an image: a function of H*W only
   float* ws_mr;
   int* sync;            // [N][3]
   int N, H, W, C1, C2, ld1, ld2, groups, act, circ_stats, circ, up, phases, halo;
@@ -263,10 +267,12 @@ __global__ void __launch_bounds__(512, 2) gn_prep_kernel(const GnPrepParams p) {
   __shared__ int s_last;
  for (int n = blockIdx.y; n < p.N; n += gridDim.y) {
   const uint16_t* src = second ? p.x2 + (size_t)n * hw * p.ld2 + (v - vecs1) * 8 : p.x1 + (size_t)n * hw * p.ld1 + v * 8;
-  // ---------------- phase 1: statistics of this CTA's band of source pixels ----------------
-  {
-    const int per = (hw + chunks - 1) / chunks;
-    const int p_begin = blockIdx.x * per, p_end = min(hw, p_begin + per);
+  // ---------------- phase 1: statistics, one slab at a time (this CTA owns slabs/chunks consecutive slabs) ----------------
+  const int cpg = C / p.groups;
+  const int slabs_per_cta = p.slabs / chunks;
+  const int per = (hw + p.slabs - 1) / p.slabs;
+  for (int sl = blockIdx.x * slabs_per_cta; sl < (blockIdx.x + 1) * slabs_per_cta; ++sl) {
+    const int p_begin = sl * per, p_end = min(hw, p_begin + per);
     float s[8], q[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
@@ -307,24 +313,24 @@ __global__ void __launch_bounds__(512, 2) gn_prep_kernel(const GnPrepParams p) {
         mine[C + v * 8 + e] = q[e];
       }
     }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-    float a = s_acc[i];
-    for (int l = 1; l < ppi; ++l) a += s_acc[(size_t)l * 2 * C + i];
-    s_acc[i] = a;
-  }
-  __syncthreads();
-  const int cpg = C / p.groups;
-  for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
-    float a = 0.f, b = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      a += s_acc[c];
-      b += s_acc[C + c];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+      float a = s_acc[i];
+      for (int l = 1; l < ppi; ++l) a += s_acc[(size_t)l * 2 * C + i];
+      s_acc[i] = a;
     }
-    float* o = p.ws + (((size_t)n * chunks + blockIdx.x) * p.groups + g) * 2;
-    o[0] = a;
-    o[1] = b;
+    __syncthreads();
+    for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
+      float a = 0.f, b = 0.f;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        a += s_acc[c];
+        b += s_acc[C + c];
+      }
+      float* o = p.ws + (((size_t)n * p.slabs + sl) * p.groups + g) * 2;
+      o[0] = a;
+      o[1] = b;
+    }
+    __syncthreads();  // s_acc is rewritten by the next slab
   }
   // ---------------- per-image barrier ----------------
   int* sync = p.sync + 3 * n;
@@ -337,8 +343,8 @@ __global__ void __launch_bounds__(512, 2) gn_prep_kernel(const GnPrepParams p) {
     __threadfence();
     for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
       double a = 0.0, b = 0.0;
-      for (int c = 0; c < chunks; ++c) {
-        const float* o = p.ws + (((size_t)n * chunks + c) * p.groups + g) * 2;
+      for (int c = 0; c < p.slabs; ++c) {
+        const float* o = p.ws + (((size_t)n * p.slabs + c) * p.groups + g) * 2;
         a += __ldcg(o);
         b += __ldcg(o + 1);
       }
@@ -620,7 +626,7 @@ extern "C" int pf_conv_prep(const void* x, void* out, int dtype, int N, int H, i
 }
 
 extern "C" int pf_gn_prep_ws_floats(int N, int groups) {
-  return N * pf::GNP_MAX_CTAS * groups * 2 + N * groups * 2;
+  return N * pf::GNP_MAX_SLABS * groups * 2 + N * groups * 2;
 }
 
 extern "C" int pf_gn_prep(const void* x1, int ld1, int C1, const void* x2, int ld2, int C2, void* cat_out, void* out,
@@ -650,7 +656,7 @@ extern "C" int pf_gn_prep(const void* x1, int ld1, int C1, const void* x2, int l
   p.out = static_cast<uint16_t*>(out);
   p.gamma = gamma; p.beta = beta;
   p.ws = ws;
-  p.ws_mr = ws + (size_t)N * GNP_MAX_CTAS * groups * 2;
+  p.ws_mr = ws + (size_t)N * GNP_MAX_SLABS * groups * 2;
   p.sync = sync;
   p.N = N; p.H = H; p.W = W; p.C1 = C1; p.C2 = C2; p.ld1 = ld1; p.ld2 = x2 ? ld2 : ld1; p.groups = groups; p.act = act;
   p.circ_stats = circ_stats; p.circ = circ; p.up = up; p.phases = phases; p.halo = halo;
@@ -665,8 +671,14 @@ extern "C" int pf_gn_prep(const void* x1, int ld1, int C1, const void* x2, int l
   p.count = float(H) * float(W + 2 * circ_stats) * float(C / groups);
   p.eps = eps;
   const int hw = H * W;
-  int chunks = hw / 16;  // >= 16 source pixels per CTA; a function of the image size ONLY (batch-invariant sums)
-  chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks);
+  int slabs = hw / 16;  // >= 16 source pixels per slab; a function of the image size ONLY (batch-invariant sums)
+  slabs = slabs < 1 ? 1 : (slabs > GNP_MAX_SLABS ? GNP_MAX_SLABS : slabs);
+  p.slabs = slabs;
+  // CTAs per image: the largest divisor of `slabs` that keeps the grid co-resident (small batch -> many CTAs per image)
+  const int cap = GNP_MAX_CTAS / (N < GNP_MAX_CTAS ? N : GNP_MAX_CTAS) > 0 ? GNP_MAX_CTAS / (N < GNP_MAX_CTAS ? N : GNP_MAX_CTAS) : 1;
+  int chunks = 1;
+  for (int d = 1; d <= slabs && d <= cap; ++d)
+    if (slabs % d == 0) chunks = d;
   const int gy = N < GNP_MAX_CTAS / chunks ? N : GNP_MAX_CTAS / chunks;
   const int vecs = C / 8;
   int ppi = 512 / vecs;

@@ -7,7 +7,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-LIMITS = {torch.float16: (3e-3, 4e-4), torch.bfloat16: (3e-2, 4e-3)}
+# measured on B200: fp16 2.5e-3 / 2.5e-4, bf16 2.3e-2 / 2.0e-3 (SD-2 size, 23 layers)
+LIMITS = {torch.float16: (5e-3, 5e-4), torch.bfloat16: (4.7e-2, 4e-3)}
 
 
 def _cmp(name, got, ref, dtype):
