@@ -130,6 +130,12 @@ typedef struct pf_gemm_args {
    *     acc <- rstd[m] * (acc - mean[m] * ln_colsum[n]) with mean / rstd from ln_stats[m][ln_slots][2] over K = Kc*num_taps
    *     elements, biased variance, eps = ln_eps — algebraically LayerNorm(A) W^T + b with the normalised tensor never
    *     stored. Supported with the plain row map and 16-bit output, or with the GEGLU epilogue. */
+  /* map_mode 1 with an output SCATTER (0 / 1 = off): the valid pixel (i, j) of image img is written to row
+   *   ((img*Hout + i-i0)*out_sy + out_a) * (Wout*out_sx) + (j-j0)*out_sx + out_b
+   * i.e. phase (out_a, out_b) of an image up-sampled by (out_sy, out_sx). Upsample2D's nearest-x2 followed by a 3x3
+   * convolution (MVGenModel.py:272-277) is exactly four 2x2 convolutions of the ORIGINAL image, one per output phase, with
+   * summed weights: 16 instead of 36 tap-GEMMs per input pixel and no up-sampled copy. */
+  int32_t out_sy, out_sx, out_a, out_b;
   float* row_stats_out;
   const float* ln_stats;
   int32_t ln_slots;
@@ -215,13 +221,15 @@ int pf_conv_prep(const void* x, void* out, int dtype, int N, int H, int W, int C
  *   gamma / beta (+ SiLU) while building the conv_prep layout (circ, up, phases, halo as in pf_conv_prep).
  * The kernel holds a per-image barrier between the statistics and the apply phase (the source is re-read from L2), so its
  * grid is capped at 148 CTAs of <= 512 threads — two such launches (the two UNet branches' streams) are always co-resident.
+ * schedule: 1 = that fused launch, 2 = two launches (statistics with one CTA per slab, then the apply pass: no barrier, many
+ * more CTAs per image — faster for the 1-2 image batches of a sharded rank), 0 = pick by N. Same bits either way.
  * ws: pf_gn_prep_ws_floats(N, groups) floats of scratch; sync: 3*N ints that are ZERO on entry (restored to zero by the
  * kernel; concurrent launches need distinct slots). The partition of every sum depends on H*W only, never on N: results are
  * bit-identical for any batch size. */
 int pf_gn_prep_ws_floats(int N, int groups);
 int pf_gn_prep(const void* x1, int ld1, int C1, const void* x2, int ld2, int C2, void* cat_out, void* out, int dtype,
                int N, int H, int W, int groups, float eps, const float* gamma, const float* beta, int act,
-               int circ_stats, int circ, int up, int phases, int halo, float* ws, int* sync, void* stream);
+               int circ_stats, int circ, int up, int phases, int halo, int schedule, float* ws, int* sync, void* stream);
 
 /* out[t, :] = LayerNorm(x[t, :] + pe[t % pe_rows, :]) * gamma + beta (pe fp32, may be NULL);
  * models/modules/transformer.py:157-160 (EPPA norm1 on x + query_pe / context, norm2) and the diffusers

@@ -36,6 +36,7 @@ class GemmArgs(C.Structure):
         ("map_mode", C.c_int32), ("Hm", C.c_int32), ("Wm", C.c_int32), ("i0", C.c_int32), ("j0", C.c_int32),
         ("Hout", C.c_int32), ("Wout", C.c_int32),
         ("k_splits", C.c_int32), ("splitk_ws", C.c_void_p),
+        ("out_sy", C.c_int32), ("out_sx", C.c_int32), ("out_a", C.c_int32), ("out_b", C.c_int32),
         ("row_stats_out", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_slots", C.c_int32), ("ln_colsum", C.c_void_p),
         ("ln_eps", C.c_float),
     ]

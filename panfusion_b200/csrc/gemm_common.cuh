@@ -22,6 +22,7 @@ struct GemmKernelParams {
   int res_f32;
   int act;
   int map_mode, Hm, Wm, i0, j0, Hout, Wout;
+  int osy, osx, oa, ob;  // output scatter of map_mode 1: row ((img*Hout + i-i0)*osy + oa), column ((j-j0)*osx + ob)
   int k_splits;     // > 1: blockIdx.y = split index, raw fp32 partials go to ws
   float* ws;        // [k_splits][M][N]
   // fused LayerNorm (see pf_gemm_args): producer side / consumer side

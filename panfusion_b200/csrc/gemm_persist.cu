@@ -183,7 +183,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int i = r / p.Wm;
         const int j = r - i * p.Wm;
         valid = valid && i >= p.i0 && i < p.i0 + p.Hout && j >= p.j0 && j < p.j0 + p.Wout;
-        orow = ((long long)img * p.Hout + (i - p.i0)) * p.Wout + (j - p.j0);
+        orow = ((long long)img * p.Hout * p.osy + (i - p.i0) * p.osy + p.oa) * (p.Wout * p.osx) + (j - p.j0) * p.osx + p.ob;
         group = img;
       } else if (p.rowbias) {
         group = m / p.rows_per_group;
@@ -322,8 +322,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   }
                 }
 #pragma unroll
-                for (int e = 0; e < 16; ++e)
-                  o[e] = (__uint_as_float(va[e]) + ba[e]) * gelu_erf_f(__uint_as_float(vg[e]) + bg[e]);
+                for (int e = 0; e < 16; e += 2)  // two columns per FFMA2 / FMUL2 / FADD2 (bit-identical to gelu_erf_f)
+                  geglu_pair(__uint_as_float(va[e]), __uint_as_float(va[e + 1]), __uint_as_float(vg[e]),
+                             __uint_as_float(vg[e + 1]), ba[e], ba[e + 1], bg[e], bg[e + 1], o[e], o[e + 1]);
                 if (p.out_f32) {
                   float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.out_ld + on0 + c);
 #pragma unroll

@@ -183,7 +183,7 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int i = r / p.Wm;
       const int j = r - i * p.Wm;
       valid = valid && i >= p.i0 && i < p.i0 + p.Hout && j >= p.j0 && j < p.j0 + p.Wout;
-      orow = ((long long)img * p.Hout + (i - p.i0)) * p.Wout + (j - p.j0);
+      orow = ((long long)img * p.Hout * p.osy + (i - p.i0) * p.osy + p.oa) * (p.Wout * p.osx) + (j - p.j0) * p.osx + p.ob;
       group = img;
     } else if (p.rowbias) {
       group = m / p.rows_per_group;
@@ -336,8 +336,9 @@ gemm_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              o[e] = (__uint_as_float(va[e]) + ba[e]) * gelu_erf_f(__uint_as_float(vg[e]) + bg[e]);
+            for (int e = 0; e < 16; e += 2)  // two columns per FFMA2 / FMUL2 / FADD2 (bit-identical to gelu_erf_f)
+              geglu_pair(__uint_as_float(va[e]), __uint_as_float(va[e + 1]), __uint_as_float(vg[e]),
+                         __uint_as_float(vg[e + 1]), ba[e], ba[e + 1], bg[e], bg[e + 1], o[e], o[e + 1]);
             if (p.out_f32) {
               float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.out_ld + on0 + c);
 #pragma unroll
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmKernelPara
     const int i = r / p.Wm;
     const int j = r - i * p.Wm;
     valid = i >= p.i0 && i < p.i0 + p.Hout && j >= p.j0 && j < p.j0 + p.Wout;
-    orow = ((long long)img * p.Hout + (i - p.i0)) * p.Wout + (j - p.j0);
+    orow = ((long long)img * p.Hout * p.osy + (i - p.i0) * p.osy + p.oa) * (p.Wout * p.osx) + (j - p.j0) * p.osx + p.ob;
     group = img;
   } else if (p.rowbias) {
     group = m / p.rows_per_group;
@@ -736,6 +737,10 @@ extern "C" int pf_gemm_taps(const pf_gemm_args* a, void* stream) {
   if (a->map_mode == 1) {
     PF_CHECK_ARG(a->Hm > 0 && a->Wm > 0 && a->Hout > 0 && a->Wout > 0 && a->M % (a->Hm * a->Wm) == 0,
                  "pf_gemm_taps: bad image map Hm=%d Wm=%d M=%d", a->Hm, a->Wm, a->M);
+    PF_CHECK_ARG(a->out_sy >= 0 && a->out_sx >= 0 && a->out_a >= 0 && a->out_b >= 0 &&
+                     a->out_a < (a->out_sy > 0 ? a->out_sy : 1) && a->out_b < (a->out_sx > 0 ? a->out_sx : 1),
+                 "pf_gemm_taps: bad output scatter (%d,%d) phase (%d,%d)", a->out_sy, a->out_sx, a->out_a, a->out_b);
+    PF_CHECK_ARG((a->out_sy <= 1 && a->out_sx <= 1) || !a->residual, "pf_gemm_taps: the scattered output map takes no residual");
   } else {
     PF_CHECK_ARG(a->map_mode == 0, "pf_gemm_taps: unknown map_mode %d", a->map_mode);
     PF_CHECK_ARG(!a->rowbias || a->rows_per_group > 0, "pf_gemm_taps: rowbias needs rows_per_group");
@@ -765,6 +770,10 @@ extern "C" int pf_gemm_taps(const pf_gemm_args* a, void* stream) {
   kp.j0 = a->j0;
   kp.Hout = a->Hout;
   kp.Wout = a->Wout;
+  kp.osy = a->out_sy > 0 ? a->out_sy : 1;
+  kp.osx = a->out_sx > 0 ? a->out_sx : 1;
+  kp.oa = a->out_a;
+  kp.ob = a->out_b;
   kp.k_splits = a->k_splits > 1 ? a->k_splits : 1;
   kp.ws = a->splitk_ws;
   kp.row_stats = a->row_stats_out;

@@ -250,7 +250,11 @@ struct GnPrepParams {
   float count, eps;
 };
 
-template <bool BF16>
+// MODE 0: fused (statistics, per-image barrier, apply) — large batches. MODE 1: statistics only, one CTA per slab, the last
+// CTA of an image finalises mean / rstd. MODE 2: apply only (reads mean / rstd), any number of CTAs per image. 1 + 2 are two
+// launches without a barrier and with far more CTAs per image: faster for the small batches of a sharded rank. The
+// statistics code is shared, so all modes produce the same bits.
+template <bool BF16, int MODE>
 __global__ void __launch_bounds__(512, 2) gn_prep_kernel(const GnPrepParams p) {
   extern __shared__ float s_acc[];  // phase 1: [ppi][2][C] partials; phase 2: [2][C] scale / shift
   pdl_launch_dependents();
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(512, 2) gn_prep_kernel(const GnPrepParams p) {
   const uint16_t* src = second ? p.x2 + (size_t)n * hw * p.ld2 + (v - vecs1) * 8 : p.x1 + (size_t)n * hw * p.ld1 + v * 8;
   // ---------------- phase 1: statistics, one slab at a time (this CTA owns slabs/chunks consecutive slabs) ----------------
   const int cpg = C / p.groups;
-  const int slabs_per_cta = p.slabs / chunks;
+  const int slabs_per_cta = MODE == 2 ? 0 : p.slabs / chunks;
   const int per = (hw + p.slabs - 1) / p.slabs;
   for (int sl = blockIdx.x * slabs_per_cta; sl < (blockIdx.x + 1) * slabs_per_cta; ++sl) {
     const int p_begin = sl * per, p_end = min(hw, p_begin + per);
@@ -334,11 +338,12 @@ __global__ void __launch_bounds__(512, 2) gn_prep_kernel(const GnPrepParams p) {
   }
   // ---------------- per-image barrier ----------------
   int* sync = p.sync + 3 * n;
+  float* mr = p.ws_mr + (size_t)n * p.groups * 2;
+  if constexpr (MODE != 2) {
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(&sync[0], 1) == chunks - 1);
   __syncthreads();
-  float* mr = p.ws_mr + (size_t)n * p.groups * 2;
   if (s_last) {
     __threadfence();
     for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
@@ -356,8 +361,12 @@ __global__ void __launch_bounds__(512, 2) gn_prep_kernel(const GnPrepParams p) {
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) st_release_s32(&sync[1], 1);
-  } else {
+    if constexpr (MODE == 1) {
+      if (threadIdx.x == 0) sync[0] = 0;  // re-armed for the next launch; the apply kernel is ordered by the stream
+    } else {
+      if (threadIdx.x == 0) st_release_s32(&sync[1], 1);
+    }
+  } else if constexpr (MODE == 0) {
     if (threadIdx.x == 0) {
       unsigned spins = 0;
       while (ld_acquire_s32(&sync[1]) == 0) {
@@ -370,6 +379,8 @@ __global__ void __launch_bounds__(512, 2) gn_prep_kernel(const GnPrepParams p) {
     }
     __syncthreads();
   }
+  }
+  if constexpr (MODE == 1) continue;
   // scale / shift of this image into shared memory (aliases the phase-1 partials)
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
@@ -380,7 +391,7 @@ __global__ void __launch_bounds__(512, 2) gn_prep_kernel(const GnPrepParams p) {
   }
   __syncthreads();
   // everyone has read mean / rstd: the last CTA to get here re-arms the image's barrier for the next launch
-  if (threadIdx.x == 0) {
+  if (MODE == 0 && threadIdx.x == 0) {
     if (atomicAdd(&sync[2], 1) == chunks - 1) {
       sync[0] = 0;
       sync[2] = 0;
@@ -631,8 +642,8 @@ extern "C" int pf_gn_prep_ws_floats(int N, int groups) {
 
 extern "C" int pf_gn_prep(const void* x1, int ld1, int C1, const void* x2, int ld2, int C2, void* cat_out, void* out,
                           int dtype, int N, int H, int W, int groups, float eps, const float* gamma, const float* beta,
-                          int act, int circ_stats, int circ, int up, int phases, int halo, float* ws, int* sync,
-                          void* stream) {
+                          int act, int circ_stats, int circ, int up, int phases, int halo, int schedule, float* ws,
+                          int* sync, void* stream) {
   using namespace pf;
   PF_CHECK_ARG(x1 && out && gamma && beta && ws && sync, "pf_gn_prep: null pointer");
   PF_CHECK_ARG(dtype == PF_BF16 || dtype == PF_F16, "pf_gn_prep: 16-bit dtype required");
@@ -674,21 +685,42 @@ extern "C" int pf_gn_prep(const void* x1, int ld1, int C1, const void* x2, int l
   int slabs = hw / 16;  // >= 16 source pixels per slab; a function of the image size ONLY (batch-invariant sums)
   slabs = slabs < 1 ? 1 : (slabs > GNP_MAX_SLABS ? GNP_MAX_SLABS : slabs);
   p.slabs = slabs;
-  // CTAs per image: the largest divisor of `slabs` that keeps the grid co-resident (small batch -> many CTAs per image)
-  const int cap = GNP_MAX_CTAS / (N < GNP_MAX_CTAS ? N : GNP_MAX_CTAS) > 0 ? GNP_MAX_CTAS / (N < GNP_MAX_CTAS ? N : GNP_MAX_CTAS) : 1;
-  int chunks = 1;
-  for (int d = 1; d <= slabs && d <= cap; ++d)
-    if (slabs % d == 0) chunks = d;
-  const int gy = N < GNP_MAX_CTAS / chunks ? N : GNP_MAX_CTAS / chunks;
   const int vecs = C / 8;
   int ppi = 512 / vecs;
   if (ppi < 1) ppi = 1;
   const int threads = vecs * ppi;
   const size_t smem = 2 * (size_t)C * ppi * sizeof(float);  // <= 32 KB
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dim3 grid(chunks, gy);
-  if (dtype == PF_BF16) launch_pdl(gn_prep_kernel<true>, grid, dim3(threads), smem, st, p);
-  else launch_pdl(gn_prep_kernel<false>, grid, dim3(threads), smem, st, p);
+  // Large batches: ONE launch with the per-image barrier (grid capped to stay co-resident). Small batches (a sharded rank:
+  // 1-2 images per branch): statistics with one CTA per slab, then the apply pass with up to 64 CTAs per image — the
+  // barrier's latency and the capped grid cost more than the second launch saves. PF_GN_FUSED_MIN_N moves the switch.
+  static const int fused_min_n = [] {
+    const char* e = getenv("PF_GN_FUSED_MIN_N");
+    return e ? atoi(e) : 8;
+  }();
+  PF_CHECK_ARG(schedule >= 0 && schedule <= 2, "pf_gn_prep: schedule must be 0 (auto), 1 (fused) or 2 (two launches)");
+  if (schedule == 1 || (schedule == 0 && N >= fused_min_n)) {
+    // CTAs per image: the largest divisor of `slabs` that keeps the grid co-resident
+    const int cap = GNP_MAX_CTAS / (N < GNP_MAX_CTAS ? N : GNP_MAX_CTAS) > 0 ? GNP_MAX_CTAS / (N < GNP_MAX_CTAS ? N : GNP_MAX_CTAS) : 1;
+    int chunks = 1;
+    for (int d = 1; d <= slabs && d <= cap; ++d)
+      if (slabs % d == 0) chunks = d;
+    const int gy = N < GNP_MAX_CTAS / chunks ? N : GNP_MAX_CTAS / chunks;
+    dim3 grid(chunks, gy);
+    if (dtype == PF_BF16) launch_pdl(gn_prep_kernel<true, 0>, grid, dim3(threads), smem, st, p);
+    else launch_pdl(gn_prep_kernel<false, 0>, grid, dim3(threads), smem, st, p);
+  } else {
+    dim3 g1(slabs, N);
+    if (dtype == PF_BF16) launch_pdl(gn_prep_kernel<true, 1>, g1, dim3(threads), smem, st, p);
+    else launch_pdl(gn_prep_kernel<false, 1>, g1, dim3(threads), smem, st, p);
+    PF_CHECK_LAUNCH("gn_prep_kernel(stats)");
+    const int total = phases * p.Ho * p.Wo;
+    int c2 = total / 32;  // >= 32 output positions per CTA
+    c2 = c2 < 1 ? 1 : (c2 > 64 ? 64 : c2);
+    dim3 g2(c2, N);
+    if (dtype == PF_BF16) launch_pdl(gn_prep_kernel<true, 2>, g2, dim3(threads), smem, st, p);
+    else launch_pdl(gn_prep_kernel<false, 2>, g2, dim3(threads), smem, st, p);
+  }
   PF_CHECK_LAUNCH("gn_prep_kernel");
   return PF_OK;
 }

@@ -357,6 +357,62 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return fmaf(hx, erf_as_f(x * 0.70710678118654752440f), hx);
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 — two IEEE fp32 operations per issued instruction) ----------
+// The GEGLU epilogue is ISSUE-bound (one erf-GELU per output element): evaluating two neighbouring columns per instruction
+// halves its FMA-pipe instruction count. Each lane rounds exactly like the scalar instruction, so results are bit-identical.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack_f2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(f32x2 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma_f2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul_f2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add_f2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// (a0 + ba0) * gelu(g0 + bg0), (a1 + ba1) * gelu(g1 + bg1): the operation sequence of gelu_erf_f / erf_as_f, two lanes wide
+__device__ __forceinline__ void geglu_pair(float a0, float a1, float g0, float g1, float ba0, float ba1, float bg0, float bg1,
+                                           float& o0, float& o1) {
+  const f32x2 x = add_f2(pack_f2(g0, g1), pack_f2(bg0, bg1));
+  const f32x2 val = add_f2(pack_f2(a0, a1), pack_f2(ba0, ba1));
+  const f32x2 xs = mul_f2(x, pack_f2(0.70710678118654752440f, 0.70710678118654752440f));
+  float xs0, xs1;
+  unpack_f2(xs, xs0, xs1);
+  const float ax0 = fabsf(xs0), ax1 = fabsf(xs1);
+  const f32x2 ax = pack_f2(ax0, ax1);
+  float d0, d1;
+  unpack_f2(fma_f2(pack_f2(0.3275911f, 0.3275911f), ax, pack_f2(1.0f, 1.0f)), d0, d1);
+  const f32x2 t = pack_f2(rcp_approx(d0), rcp_approx(d1));
+  f32x2 p = fma_f2(pack_f2(1.061405429f, 1.061405429f), t, pack_f2(-1.453152027f, -1.453152027f));
+  p = fma_f2(p, t, pack_f2(1.421413741f, 1.421413741f));
+  p = fma_f2(p, t, pack_f2(-0.284496736f, -0.284496736f));
+  p = fma_f2(p, t, pack_f2(0.254829592f, 0.254829592f));
+  float e0, e1;
+  unpack_f2(mul_f2(ax, mul_f2(ax, pack_f2(-1.4426950408889634f, -1.4426950408889634f))), e0, e1);
+  const f32x2 ex = pack_f2(ex2_approx(e0), ex2_approx(e1));
+  // r = fma(-p*t, ex, 1)
+  const f32x2 npt = mul_f2(mul_f2(p, pack_f2(-1.0f, -1.0f)), t);
+  float r0, r1;
+  unpack_f2(fma_f2(npt, ex, pack_f2(1.0f, 1.0f)), r0, r1);
+  const f32x2 erfv = pack_f2(copysignf(r0, xs0), copysignf(r1, xs1));
+  const f32x2 hx = mul_f2(x, pack_f2(0.5f, 0.5f));
+  unpack_f2(mul_f2(val, fma_f2(hx, erfv, hx)), o0, o1);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

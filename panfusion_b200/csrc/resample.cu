@@ -176,7 +176,7 @@ template <> struct Quad<__nv_bfloat16> {
 };
 
 template <typename T, bool P2E, int QPT>
-__global__ void __launch_bounds__(STG_THREADS, QPT == 1 ? 3 : 2)
+__global__ void __launch_bounds__(STG_THREADS, 2)
 resample_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, uint8_t* __restrict__ mask_out, int C,
                      int Hs, int Ws, int Hd, int Wd, const double* __restrict__ cams, int cam_stride, int mode,
                      int ch_per_cta, int ch_per_stage, int src_repeat, int tile_px) {
@@ -215,14 +215,12 @@ resample_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, uint8_t* __
   }
 
   const double* cam = cams + (size_t)b * cam_stride * PF_CAM_DOUBLES;
-  Taps taps[QPT][4];   // idx holds BYTE offsets into a source plane after the set-up below (-1 = dropped tap)
+  Taps taps[QPT][4];
   bool any_live[QPT];
-  uint32_t interior[QPT];  // bit j: all four taps of pixel j are inside the image (branch-free bilinear)
 #pragma unroll
   for (int i = 0; i < QPT; ++i) {
     const int q0 = pix0 + 4 * (threadIdx.x + i * STG_THREADS);
     any_live[i] = false;
-    interior[i] = 0;
     uint32_t mbits = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -241,15 +239,8 @@ resample_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, uint8_t* __
         }
       }
       make_taps(px, py, Hs, Ws, mode, live, taps[i][j]);
-      bool all4 = true;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const bool ok = taps[i][j].idx[k] >= 0;
-        any_live[i] = any_live[i] || ok;
-        all4 = all4 && ok;
-        if (ok) taps[i][j].idx[k] *= int(sizeof(T));
-      }
-      interior[i] |= (all4 ? 1u : 0u) << j;
+      for (int k = 0; k < 4; ++k) any_live[i] = any_live[i] || taps[i][j].idx[k] >= 0;
     }
     if constexpr (P2E) {
       if (mask_out && blockIdx.x == 0 && q0 < pix_end)
@@ -263,32 +254,24 @@ resample_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, uint8_t* __
     const int ca = c_begin + st * ch_per_stage;
     const int nch = min(ch_per_stage, c_end - ca);
     T* dp = dst + ((size_t)b * C + ca) * dplane;
-    const char* sp = reinterpret_cast<const char*>(sb);
-    const int plane_bytes = splane * int(sizeof(T));
-    T* dq = dp + pix0 + 4 * threadIdx.x;
-    for (int ch = 0; ch < nch; ++ch, sp += plane_bytes, dq += dplane) {
-      auto at = [&](int off) { return Cvt<T>::to_f(*reinterpret_cast<const T*>(sp + off)); };
+    for (int ch = 0; ch < nch; ++ch) {
+      const T* sp = sb + (size_t)ch * splane;
 #pragma unroll
       for (int i = 0; i < QPT; ++i) {
-        if (pix0 + 4 * (threadIdx.x + i * STG_THREADS) < pix_end) {
+        const int q0 = pix0 + 4 * (threadIdx.x + i * STG_THREADS);
+        if (q0 < pix_end) {
           float o[4] = {0.f, 0.f, 0.f, 0.f};
           if (any_live[i]) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const Taps& t = taps[i][j];
-              if ((interior[i] >> j) & 1u) {
-                // same operation order as the general path (0 + v0*w0 is exact), no per-tap branches
-                o[j] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(at(t.idx[0]), t.w[0]), __fmul_rn(at(t.idx[1]), t.w[1])),
-                                           __fmul_rn(at(t.idx[2]), t.w[2])), __fmul_rn(at(t.idx[3]), t.w[3]));
-              } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (t.idx[k] >= 0) o[j] = __fadd_rn(o[j], __fmul_rn(at(t.idx[k]), t.w[k]));
-                }
+              for (int k = 0; k < 4; ++k) {
+                if (taps[i][j].idx[k] >= 0)
+                  o[j] = __fadd_rn(o[j], __fmul_rn(Cvt<T>::to_f(sp[taps[i][j].idx[k]]), taps[i][j].w[k]));
               }
             }
           }
-          Quad<T>::store(dq + 4 * i * STG_THREADS, o);
+          Quad<T>::store(dp + (size_t)ch * dplane + q0, o);
         }
       }
     }
@@ -306,18 +289,15 @@ static int launch_resample(const void* src, void* dst, uint8_t* mask, int B, int
   // quad path: vector stores need a 4-pixel-aligned output plane; the mask is written 4 bytes at a time
   if (aligned && plane_bytes <= 48 * 1024 && C >= 4 && Wd % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 &&
       (!mask || (reinterpret_cast<uintptr_t>(mask) & 3) == 0) && B <= 65535) {
-    // one quad (4 pixels) per thread and 32 KB stages -> three co-resident CTAs per SM: the gathers are latency-bound, and
-    // halving the pixels per thread halves the fp64 grid set-up that every channel group of a camera repeats
-    const bool small_plane = plane_bytes <= 32 * 1024;
-    int ch_per_stage = (int)(((small_plane ? 32 : 48) * 1024) / plane_bytes);
+    int ch_per_stage = (int)((48 * 1024) / plane_bytes);
     if (ch_per_stage > 16) ch_per_stage = 16;
-    const int max_tile = 4 * (small_plane ? 1 : 2) * STG_THREADS;
+    const int max_tile = 4 * 2 * STG_THREADS;  // QPT = 2
     const int tiles = (dplane + max_tile - 1) / max_tile;
     int tile_px = (dplane + tiles - 1) / tiles;
     tile_px = (tile_px + 3) & ~3;
     const int qpt = (tile_px + 4 * STG_THREADS - 1) / (4 * STG_THREADS);
-    // exactly ONE wave of co-resident CTAs when the problem allows it
-    int ctas_per_bt = (148 * (qpt <= 1 ? 3 : 2)) / (B * tiles);
+    // exactly ONE wave of co-resident CTAs (2 per SM) when the problem allows it
+    int ctas_per_bt = (148 * 2) / (B * tiles);
     if (ctas_per_bt < 1) ctas_per_bt = 1;
     int ch_per_cta = (C + ctas_per_bt - 1) / ctas_per_bt;
     ch_per_cta = ((ch_per_cta + ch_per_stage - 1) / ch_per_stage) * ch_per_stage;

@@ -16,7 +16,7 @@ import torch
 from torch import Tensor
 
 from . import ops
-from .packing import pack_conv3x3, pack_geglu
+from .packing import pack_conv3x3, pack_geglu, pack_upsample_phases
 
 
 @dataclass
@@ -91,6 +91,17 @@ class _Conv3:
         self.w = pack_conv3x3(conv.weight.detach()).to(dev, dt).contiguous()
         self.b = conv.bias.detach().to(dev, torch.float32).contiguous() if conv.bias is not None else None
         self.cout, self.cin = conv.weight.shape[0], conv.weight.shape[1]
+
+
+# Upsample2D (nearest x2 + 3x3 conv) as four 2x2 phase convolutions of the original-resolution image (2.25x fewer MACs, no
+# up-sampled copy); PF_UPSAMPLE_PHASES=0 keeps the literal nearest-x2 + 9-tap path for A/B checks
+UPSAMPLE_PHASES = __import__("os").environ.get("PF_UPSAMPLE_PHASES", "1") != "0"
+
+
+class _Up(_Conv3):
+    def __init__(self, conv, dev, dt):
+        super().__init__(conv, dev, dt)
+        self.phase_w = [w.to(dev, dt).contiguous() for w in pack_upsample_phases(conv.weight)]
 
 
 class _Resnet:
@@ -181,7 +192,7 @@ class UNetPack:
             self.up.append(dict(
                 resnets=[res(r) for r in blk.resnets],
                 attns=[tr(t) for t in blk.attentions] if has_attn else None,
-                up=[_Conv3(u.conv, dev, dt) for u in blk.upsamplers] if blk.upsamplers is not None else None))
+                up=[_Up(u.conv, dev, dt) for u in blk.upsamplers] if blk.upsamplers is not None else None))
         # one GEMM for every ResnetBlock2D.time_emb_proj (applied to silu(temb))
         off, ws, bs = 0, [], []
         for p in self.resnets:
@@ -372,17 +383,31 @@ class Branch:
         ops.gemm_taps(a, d.w, out, M=PS, Kc=d.cin, taps=taps, bias=d.b, image_map=(Hq, Wq, 0, crop, Ho, Wout))
         return Img(out, N, Ho, Wout)
 
-    def upsample(self, x: Img, u: _Conv3) -> Img:
-        """Upsample2D (nearest x2 -> 3x3 conv); panorama: pad_pano(1) -> up -> unpad_pano(2) (MVGenModel.py:272-277)."""
+    def upsample(self, x: Img, u: "_Up") -> Img:
+        """Upsample2D (nearest x2 -> 3x3 conv); panorama: pad_pano(1) -> up -> unpad_pano(2) (MVGenModel.py:272-277).
+        Output pixel (2i+a, 2j+b) depends on a 2x2 neighbourhood of the ORIGINAL image only, so the layer runs as four
+        4-tap GEMMs over the zero-haloed original image, each scattering its phase into the 2x larger output."""
         c = 1 if self.circ else 0
         N, H, W = x.N, x.H, x.W
-        a = ops.conv_prep(x.t, N, H, W, circ=c, up=2, halo=1)
-        Hu, Wu = 2 * H, 2 * (W + 2 * c)
-        Hp, Wp = Hu + 2, Wu + 2
-        out = torch.empty((N * Hu * 2 * W, u.cout), dtype=self.dt, device=x.t.device)
-        ops.gemm_taps(a, u.w, out, M=N * Hp * Wp, Kc=u.cin, taps=taps3x3(Wp), bias=u.b,
-                      image_map=(Hp, Wp, 1, 1 + 2 * c, Hu, 2 * W))
-        return Img(out, N, Hu, 2 * W)
+        if not UPSAMPLE_PHASES:
+            a = ops.conv_prep(x.t, N, H, W, circ=c, up=2, halo=1)
+            Hu, Wu = 2 * H, 2 * (W + 2 * c)
+            Hp, Wp = Hu + 2, Wu + 2
+            out = torch.empty((N * Hu * 2 * W, u.cout), dtype=self.dt, device=x.t.device)
+            ops.gemm_taps(a, u.w, out, M=N * Hp * Wp, Kc=u.cin, taps=taps3x3(Wp), bias=u.b,
+                          image_map=(Hp, Wp, 1, 1 + 2 * c, Hu, 2 * W))
+            return Img(out, N, Hu, 2 * W)
+        a = ops.conv_prep(x.t, N, H, W, circ=c, up=1, halo=1)
+        Hp, Wp = H + 2, W + 2 * c + 2
+        out = torch.empty((N * 2 * H * 2 * W, u.cout), dtype=self.dt, device=x.t.device)
+        k = 0
+        for pa in (0, 1):
+            for pb in (0, 1):
+                taps = [(pa + r - 1) * Wp + (pb + cc - 1) for r in (0, 1) for cc in (0, 1)]
+                ops.gemm_taps(a, u.phase_w[k], out, M=N * Hp * Wp, Kc=u.cin, taps=taps, bias=u.b,
+                              image_map=(Hp, Wp, 1, 1 + c, H, W), scatter=(2, 2, pa, pb))
+                k += 1
+        return Img(out, N, 2 * H, 2 * W)
 
     def concat(self, a: Img, b: Img) -> Img:
         """torch.cat([hidden, skip], dim=1) in channels-last layout."""

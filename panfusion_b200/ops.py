@@ -57,7 +57,7 @@ def gemm_taps(A: Tensor, B: Tensor, out: Tensor, *, M: int, Kc: int, taps: Seque
               bias: Optional[Tensor] = None, rowbias: Optional[Tensor] = None, rows_per_group: int = 0,
               residual: Optional[Tensor] = None, act: int = PF_ACT_NONE,
               image_map: Optional[tuple] = None, block_n: int = 0, k_splits: Optional[int] = None,
-              row_stats: bool = False, ln: Optional[tuple] = None):
+              row_stats: bool = False, ln: Optional[tuple] = None, scatter: Optional[tuple] = None):
     """acc = sum_t A[m + taps[t], :Kc] @ B[:, t*Kc:(t+1)*Kc]^T ; see include/panfusion_b200.h (pf_gemm_taps).
 
     A: [a_rows, a_ld] 16-bit, B: [N, len(taps)*Kc] 16-bit packed weight, out: [rows, n_out].
@@ -100,6 +100,8 @@ def gemm_taps(A: Tensor, B: Tensor, out: Tensor, *, M: int, Kc: int, taps: Seque
     if image_map is not None:
         a.map_mode = 1
         a.Hm, a.Wm, a.i0, a.j0, a.Hout, a.Wout = (int(v) for v in image_map)
+        if scatter is not None:  # (sy, sx, a, b): write phase (a, b) of the (sy, sx)-times larger output image
+            a.out_sy, a.out_sx, a.out_a, a.out_b = (int(v) for v in scatter)
     stats = None
     if row_stats:
         slots = int(_lib.lib().pf_gemm_row_stats_slots(C.byref(a)))
@@ -225,9 +227,12 @@ def conv_prep(x: Tensor, N: int, H: int, W: int, *, stats: Optional[Tensor] = No
     return out
 
 
+GN_FUSED_MIN_N = int(__import__("os").environ.get("PF_GN_FUSED_MIN_N", "8"))  # mirrors the switch inside pf_gn_prep
+
+
 def gn_prep(x: Tensor, N: int, H: int, W: int, *, gamma: Tensor, beta: Tensor, groups: int, eps: float,
             act: int = PF_ACT_NONE, circ_stats: int = 0, circ: int = 0, up: int = 1, phases: int = 1, halo: int = 1,
-            x2: Optional[Tensor] = None, want_cat: bool = False):
+            x2: Optional[Tensor] = None, want_cat: bool = False, schedule: int = 0):
     """GroupNorm statistics + apply (+SiLU) + conv_prep layout in one launch (pf_gn_prep); with x2 the normalised tensor
     is the channel concatenation cat(x, x2) and want_cat also returns that raw concatenation.
     -> out [phases * N * Ho * Wo, C] (and cat [N*H*W, C] if want_cat)."""
@@ -242,10 +247,11 @@ def gn_prep(x: Tensor, N: int, H: int, W: int, *, gamma: Tensor, beta: Tensor, g
     out = torch.empty((phases * N * Ho * Wo, Cc), dtype=x.dtype, device=x.device)
     cat = torch.empty((N * H * W, Cc), dtype=x.dtype, device=x.device) if want_cat else None
     ws = torch.empty(lib.pf_gn_prep_ws_floats(N, groups), dtype=torch.float32, device=x.device)
-    _count(1)
+    _count(1 if (schedule == 1 or (schedule == 0 and N >= GN_FUSED_MIN_N)) else 2)
     _lib.check(lib.pf_gn_prep(_vp(x), x.stride(0), C1, _vp(x2), x2.stride(0) if x2 is not None else 0, C2, _vp(cat),
                               _vp(out), _lib.dtype_code(x.dtype), N, H, W, groups, _f(eps), _vp(gamma), _vp(beta), act,
-                              circ_stats, circ, up, phases, halo, _vp(ws), _vp(_gn_counter_slot(x.device, 3 * N)), _st()))
+                              circ_stats, circ, up, phases, halo, schedule, _vp(ws),
+                              _vp(_gn_counter_slot(x.device, 3 * N)), _st()))
     return (out, cat) if want_cat else out
 
 

@@ -27,3 +27,21 @@ def pack_geglu(w: Tensor, b: Tensor | None, block_n: int):
         bp = torch.stack([bv.reshape(inner // half, half), bg.reshape(inner // half, half)], dim=1).reshape(n2)
         bp = bp.contiguous().float()
     return wp, bp
+
+
+def pack_upsample_phases(w: Tensor) -> list[Tensor]:
+    """Upsample2D = nearest x2 then a 3x3 convolution (pad 1). Output pixel (2i+a, 2j+b) only ever sees the 2x2 source
+    neighbourhood rows {i-1+a, i+a} x cols {j-1+b, j+b}; the 3x3 taps that land on the same source pixel are summed (in
+    fp32, before rounding to the compute type). -> four packed weights [Cout, 4*Cin], phase order (a, b) = (0,0), (0,1),
+    (1,0), (1,1), tap order (r, c) row-major, matching engine.taps2x2."""
+    w = w.detach().to(torch.float32)
+    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}  # phase a -> kernel rows feeding source row r = 0 / 1
+    out = []
+    for a in (0, 1):
+        for b in (0, 1):
+            taps = []
+            for r in (0, 1):
+                for c in (0, 1):
+                    taps.append(w[:, :, rows[a][r]][:, :, :, rows[b][c]].sum(dim=(2, 3)))  # [Cout, Cin]
+            out.append(torch.cat(taps, dim=1).contiguous())
+    return out

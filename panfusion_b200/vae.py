@@ -19,7 +19,7 @@ import torch
 from torch import Tensor
 
 from . import _lib, ops
-from .engine import Branch, Img, _Conv3, _Lin, _Norm, taps3x3
+from .engine import Branch, Img, _Conv3, _Lin, _Norm, _Up, taps3x3
 from .packing import pack_conv3x3
 from .pano import pad_pano, unpad_pano
 
@@ -62,7 +62,7 @@ class VAEDecoderPack:
         self.up = []
         for blk in d.up_blocks:
             self.up.append(dict(resnets=[_VResnet(r, dev, dt) for r in blk.resnets],
-                                up=[_Conv3(u.conv, dev, dt) for u in blk.upsamplers] if blk.upsamplers is not None else None))
+                                up=[_Up(u.conv, dev, dt) for u in blk.upsamplers] if blk.upsamplers is not None else None))
         self.norm_out = _Norm(d.conv_norm_out, dev)
         co = d.conv_out.weight.shape[0]
         wpad = torch.zeros((64, *d.conv_out.weight.shape[1:]), dtype=d.conv_out.weight.dtype, device=d.conv_out.weight.device)

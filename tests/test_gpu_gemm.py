@@ -204,3 +204,42 @@ def test_layernorm_fused_into_geglu(cuda_device, dtype, M, C, sched):
     err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
     print(f"[parity] fused LN->GEGLU {dtype} M={M} C={C}: max err {err:.2e} of max|ref|")
     assert err < (1.5e-2 if dtype == torch.bfloat16 else 2e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("circ", [False, True])
+def test_upsample_phase_convolutions(cuda_device, dtype, circ):
+    """Upsample2D (nearest x2 -> conv3x3, MVGenModel.py:272-277; panorama: pad_pano(1) -> up -> unpad_pano(2)) as four
+    2x2 phase convolutions with scattered output (pf_gemm_args.out_sy/out_sx) == the torch composition, and == the literal
+    nearest-x2 + 9-tap path up to the rounding of the pre-summed weights."""
+    from oracle.eppa import pad_pano
+    from panfusion_b200 import engine
+    N, C, Co, H, W = 3, 128, 192, 8, 12
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(N, C, H, W, generator=g).to(dtype)
+    conv = torch.nn.Conv2d(C, Co, 3, padding=1)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(Co, C, 3, 3, generator=g) / (9 * C) ** 0.5)
+        conv.bias.copy_(torch.randn(Co, generator=g))
+    xs = pad_pano(x.float(), 1) if circ else x.float()
+    ref = F.conv2d(F.interpolate(xs, scale_factor=2.0, mode="nearest"), conv.weight, conv.bias, padding=1)
+    ref = ref[..., 2:-2] if circ else ref
+
+    class _P:  # the two attributes Branch.upsample reads from its pack
+        dt = dtype
+    br = engine.Branch.__new__(engine.Branch)
+    br.p, br.circ, br.dt = _P(), circ, dtype
+    u = engine._Up(conv, cuda_device, dtype)
+    xt = engine.img_from_nchw(x.to(cuda_device), dtype)
+    outs = {}
+    for phases in (True, False):
+        engine.UPSAMPLE_PHASES = phases
+        try:
+            o = br.upsample(xt, u)
+        finally:
+            engine.UPSAMPLE_PHASES = True
+        assert (o.N, o.H, o.W) == (N, 2 * H, 2 * W)
+        outs[phases] = o.nchw().float().cpu()
+    tol = dict(rtol=2 ** -7, atol=3e-2) if dtype == torch.bfloat16 else dict(rtol=2 ** -10, atol=4e-3)
+    torch.testing.assert_close(outs[True], ref, **tol)
+    torch.testing.assert_close(outs[False], ref, **tol)
