@@ -222,7 +222,8 @@ int pf_conv_prep(const void* x, void* out, int dtype, int N, int H, int W, int C
  * The kernel holds a per-image barrier between the statistics and the apply phase (the source is re-read from L2), so its
  * grid is capped at 148 CTAs of <= 512 threads — two such launches (the two UNet branches' streams) are always co-resident.
  * schedule: 1 = that fused launch, 2 = two launches (statistics with one CTA per slab, then the apply pass: no barrier, many
- * more CTAs per image — faster for the 1-2 image batches of a sharded rank), 0 = pick by N. Same bits either way.
+ * more CTAs per image — measured faster at every batch size of the denoise step), 0 = default (two launches unless
+ * PF_GN_FUSED_MIN_N says otherwise). Same bits either way.
  * ws: pf_gn_prep_ws_floats(N, groups) floats of scratch; sync: 3*N ints that are ZERO on entry (restored to zero by the
  * kernel; concurrent launches need distinct slots). The partition of every sum depends on H*W only, never on N: results are
  * bit-identical for any batch size. */

@@ -698,9 +698,12 @@ extern "C" int pf_gemm_splitk_plan(const pf_gemm_args* a) {
   if (!bn) return 1;
   const long long tiles = (long long)((a->M + 127) / 128) * (a->N / bn);
   const int num_kb = a->Kc / 64 * a->num_taps;
-  if (tiles >= 148 || num_kb < 32) return 1;        // enough CTAs already, or K too short to amortise the reduce
-  int s = (int)((2 * 148 + tiles - 1) / tiles);       // aim for ~2 CTAs per SM
-  const int max_by_k = num_kb / 8;                    // >= 8 K-slabs per split
+  // Only the skinny deep-K problems: a sharded rank's 8x8 / 16x16-level convolutions have <= 60 output tiles and 90-360
+  // K-slabs, i.e. a handful of SMs each streaming megabytes of weights at the per-SM L2 rate (60-120 us per launch).
+  // Shapes that already cover half the machine, or short K, lose more to the partial-sum traffic than they gain.
+  if (tiles > 74 || num_kb < 64) return 1;
+  int s = (int)((148 + tiles - 1) / tiles);           // aim for ~1 CTA per SM
+  const int max_by_k = num_kb / 16;                   // >= 16 K-slabs per split
   if (s > max_by_k) s = max_by_k;
   if (s > 16) s = 16;
   return s < 2 ? 1 : s;

@@ -116,7 +116,7 @@ def gemm_taps(A: Tensor, B: Tensor, out: Tensor, *, M: int, Kc: int, taps: Seque
     if k_splits is None:
         k_splits = _lib.lib().pf_gemm_splitk_plan(C.byref(a)) if (SPLIT_K and not row_stats and ln is None) else 1
     if k_splits > 1:
-        a.block_n = int(block_n) & 0xffff  # split-K runs on the tile-per-CTA schedule
+        a.block_n = 0  # split-K runs on the tile-per-CTA schedule with the widest tile (operand bytes per FLOP matter)
         ws = torch.empty(k_splits * int(M) * B.shape[0], dtype=torch.float32, device=A.device)
         a.k_splits, a.splitk_ws = int(k_splits), ws.data_ptr()
         _count(1)
@@ -227,7 +227,7 @@ def conv_prep(x: Tensor, N: int, H: int, W: int, *, stats: Optional[Tensor] = No
     return out
 
 
-GN_FUSED_MIN_N = int(__import__("os").environ.get("PF_GN_FUSED_MIN_N", "8"))  # mirrors the switch inside pf_gn_prep
+GN_FUSED_MIN_N = int(__import__("os").environ.get("PF_GN_FUSED_MIN_N", str(1 << 30)))  # mirrors the switch inside pf_gn_prep
 
 
 def gn_prep(x: Tensor, N: int, H: int, W: int, *, gamma: Tensor, beta: Tensor, groups: int, eps: float,
