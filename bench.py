@@ -275,8 +275,11 @@ def run_b200(args):
     if world > 1:
         from panfusion_b200.parallel import pick_layout
         bsh, vsh = pick_layout(world, 2, wl["m"])
+        from panfusion_b200.parallel import DEVICE_GATHER
+        transport = ("device-initiated (pf_allgather_views: NVLink stores into CUDA-IPC receive buffers, inside the step's "
+                     "CUDA graph)" if DEVICE_GATHER else "NCCL between graph segments")
         parallelism = (f"{bsh} CFG shards x {vsh} view shards (one process per GPU; pano branch once per CFG shard; "
-                       f"{'one K|V all-gather per EPPA block + ' if vsh > 1 else ''}one eps all-gather per step, NCCL)")
+                       f"{'one K|V all-gather per EPPA block + ' if vsh > 1 else ''}one eps all-gather per step, {transport})")
     else:
         parallelism = "single GPU"
     if rank == 0:

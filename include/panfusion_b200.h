@@ -318,6 +318,9 @@ int pf_eppa_pe(const double* cams_e2p, int V, int ph, int pw, int eh, int ew, co
  *   my_flags      == peer_flags[rank];  state: 2 zero-initialised uint32 of this rank (epoch, CTA counter)
  * On return (stream order) the own receive buffer holds every rank's slice in rank order. One kernel: push to all peers,
  * publish the epoch, wait for all peers; a peer that never arrives makes the kernel trap after ~2 s instead of hanging. */
+/* let kernels of the CURRENT device store into memory of `peer_device` (cudaDeviceEnablePeerAccess; idempotent) — needed once
+ * per peer before pf_allgather_views pushes into IPC-mapped buffers that live on the other GPUs of the node */
+int pf_enable_peer_access(int peer_device);
 int pf_allgather_views(const void* local, long long slice_bytes, void* const* peer_data, unsigned int* const* peer_flags,
                        unsigned int* my_flags, unsigned int* state, int rank, int nranks, void* stream);
 

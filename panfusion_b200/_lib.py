@@ -82,7 +82,7 @@ EXPORTS = [
     "pf_groupnorm_ws_floats", "pf_groupnorm_stats", "pf_conv_prep", "pf_gn_prep_ws_floats", "pf_gn_prep", "pf_layernorm",
     "pf_conv_in", "pf_conv_out", "pf_copy2d", "pf_pad_pano", "pf_softmax_rows", "pf_tensor_to_image", "pf_timestep_embed", "pf_cfg_ddim_step", "pf_cfg_ddim_step_dev",
     "pf_eppa_tables", "pf_eppa_pe",
-    "pf_allgather_views", "pf_embed_tokens",
+    "pf_allgather_views", "pf_enable_peer_access", "pf_embed_tokens",
 ]
 
 

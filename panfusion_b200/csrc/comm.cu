@@ -78,6 +78,25 @@ __global__ void __launch_bounds__(256) allgather_push_wait_kernel(const AllGathe
 
 }  // namespace pf
 
+extern "C" int pf_enable_peer_access(int peer_device) {
+  using namespace pf;
+  int dev = -1;
+  if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  if (peer_device == dev) return PF_OK;
+  int can = 0;
+  if (int rc = check_cuda(cudaDeviceCanAccessPeer(&can, dev, peer_device), "cudaDeviceCanAccessPeer")) return rc;
+  if (!can) {
+    set_error("pf_enable_peer_access: device %d cannot access device %d (no NVLink / PCIe peer path)", dev, peer_device);
+    return PF_ERR_UNSUPPORTED;
+  }
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();  // clear the sticky "already enabled" status
+    return PF_OK;
+  }
+  return check_cuda(e, "cudaDeviceEnablePeerAccess");
+}
+
 extern "C" int pf_allgather_views(const void* local, long long slice_bytes, void* const* peer_data,
                                   unsigned int* const* peer_flags, unsigned int* my_flags, unsigned int* state, int rank,
                                   int nranks, void* stream) {

@@ -30,10 +30,12 @@ def _st():
 
 # per-shape tile choice measured on B200 by scripts/tune_gemm.py: (M, N, Kc, taps) -> block_n
 GEMM_LOG = None
-# Split-K (pf_gemm_splitk_plan) measured on B200 over the whole step: 33.2 steps/s with, 34.1 without — the few-tile
-# convolutions it targets already overlap with the other UNet branch's stream, so the extra partial-sum traffic is a
-# net loss. Kept (and tested) for single-branch use; opt in with PF_SPLIT_K=1 or k_splits=.
-SPLIT_K = __import__("os").environ.get("PF_SPLIT_K", "0") != "0"
+# Split-K (pf_gemm_splitk_plan: only skinny deep-K problems — <= 74 output tiles, >= 64 K-slabs, i.e. the 8x8 / 16x16-level
+# convolutions of a small batch). Measured on B200: one rank of the 8-GPU layout 10.85 -> 9.82 ms per step, its 1-image
+# panorama branch 7.54 -> 6.54 ms, single-GPU step unchanged (37.3 -> 37.4 steps/s). The K partition depends on the
+# problem's M, so a sharded rank and the single-GPU run round a few convolutions differently (fp32 summation order):
+# PF_SPLIT_K=0 (or ops.SPLIT_K = False) restores the bit-identical sharded == unsharded behaviour the tests check.
+SPLIT_K = __import__("os").environ.get("PF_SPLIT_K", "1") != "0"
 _TUNED: dict = {}
 
 

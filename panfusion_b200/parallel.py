@@ -67,6 +67,8 @@ class DeviceAllGather:
                 data_ptrs.append(site.recv.data_ptr())
                 flag_ptrs.append(site.ctrl.data_ptr())
                 continue
+            from . import _lib
+            _lib.check(_lib.lib().pf_enable_peer_access(int(handles[0][0])))  # this GPU's kernels store into that GPU
             st = [torch.UntypedStorage._new_shared_cuda(*h) for h in handles]
             site.keep.append(st)  # the mappings live as long as the site
             data_ptrs.append(st[0].data_ptr() + off[0])

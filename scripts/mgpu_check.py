@@ -72,7 +72,9 @@ def main():
         d_lat = (outs[0][0] - outs[1][0]).abs().max().item()
         d_pano = (outs[0][1] - outs[1][1]).abs().max().item()
         scale = outs[0][0].abs().max().item()
-        tol = float(os.environ.get("MGPU_TOL", "0"))  # the sharded step is bit-identical to the single-GPU one
+        # bit-identical with PF_SPLIT_K=0; the default M-dependent split-K partition changes fp32 summation order only
+        from panfusion_b200 import ops
+        tol = float(os.environ.get("MGPU_TOL", "2e-3" if ops.SPLIT_K else "0"))
         good = d_lat <= tol * scale and d_pano <= tol * scale
         ok = ok and good
         if rank == 0:

@@ -11,13 +11,16 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
+@pytest.mark.parametrize("split_k", ["0", "1"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_matches_single(world):
+def test_sharded_matches_single(world, split_k):
+    """split_k 0: the sharded sampler result must be BIT-IDENTICAL to the single-GPU one; 1 (default kernels): within 2e-3."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
+    import os
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + world), str(ROOT / "scripts" / "mgpu_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env={**os.environ, "PF_SPLIT_K": split_k})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MISMATCH" not in r.stdout
 
