@@ -210,7 +210,7 @@ class ViewParallel:
         if self.view_shards == 1:
             return x
         bl, L, C = x.shape
-        if self.device_gather:
+        if self.device_gather and x.is_cuda:  # CPU tensors (the gloo plumbing tests) take the torch.distributed path
             if self._dev_view is None:
                 self._dev_view = DeviceAllGather(self.view_group)
             out = self._dev_view.all_gather(self._next_key(), x.contiguous())
@@ -228,7 +228,7 @@ class ViewParallel:
         bl, ml = b // self.batch_shards, m // self.view_shards
         pc, grp = pano_loc.contiguous(), self.group
         s_all, sc = None, None
-        if self.device_gather:
+        if self.device_gather and pc.is_cuda:
             if self._dev_world is None:
                 self._dev_world = DeviceAllGather(self.group)
             pano_all = self._dev_world.all_gather(self._next_key(), pc)
