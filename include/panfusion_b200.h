@@ -182,12 +182,23 @@ typedef struct pf_fmha_args {
   const uint8_t* bias_flags;
   int64_t flags_bstride;
   int32_t flags_ld;
+  /* tile-PACKED bias (the resident form of the EPPA tables): `bias` is then the store [n_live][128][64] fp32 built by
+   * pf_bias_tile_pack and bias_tile_off[bias batch][ceil(Lq/128)][ceil(Lk/64)] (row stride flags_ld, batch stride
+   * flags_bstride, in tiles) holds each tile's index in it, or -1 for a tile that is entirely -1 (no correspondence).
+   * bias_ld / bias_bstride / bias_flags are unused. The reference materialises the dense tensor PER HEAD
+   * (models/modules/transformer.py:68); this keeps ~15 % of ONE copy. */
+  const int32_t* bias_tile_off;
 } pf_fmha_args;
 
 int pf_fmha_fwd(const pf_fmha_args* args, void* stream);
 /* flags[g][qt][kt] = 1 iff bias[g][qt*128 .. , kt*64 ..] is entirely == -1.0f (tiles clipped at Lq / Lk) */
 int pf_bias_tile_flags(const float* bias, int G, int Lq, int Lk, int bias_ld, int64_t bias_bstride, uint8_t* flags,
                        void* stream);
+/* exclusive scan of the live (flag == 0) tiles: tile_off[t] = index among the live tiles or -1; n_live[0] = their number */
+int pf_bias_tile_scan(const uint8_t* flags, int num_tiles, int32_t* tile_off, int32_t* n_live, void* stream);
+/* packed[tile_off[g][qt][kt]][128][64] <- the dense 128 x 64 tile (zero outside [Lq, Lk]); constant tiles are skipped */
+int pf_bias_tile_pack(const float* bias, int G, int Lq, int Lk, int bias_ld, int64_t bias_bstride, const int32_t* tile_off,
+                      float* packed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm statistics of a channels-last image x[N, H, W, C] (row stride ld), computed over the image
@@ -318,6 +329,13 @@ int pf_eppa_pe(const double* cams_e2p, int V, int ph, int pw, int eh, int ew, co
  *   my_flags      == peer_flags[rank];  state: 2 zero-initialised uint32 of this rank (epoch, CTA counter)
  * On return (stream order) the own receive buffer holds every rank's slice in rank order. One kernel: push to all peers,
  * publish the epoch, wait for all peers; a peer that never arrives makes the kernel trap after ~2 s instead of hanging. */
+/* Receive buffers of the device-side collectives: cudaMalloc'ed (zero-filled) by pf_comm_alloc, exported as a 64-byte CUDA IPC
+ * handle, opened by the peers ON THEIR device (cudaIpcOpenMemHandle with lazy peer access — NVLink on an HGX board). */
+int pf_comm_alloc(long long bytes, void** ptr);
+int pf_comm_free(void* ptr);
+int pf_ipc_export(const void* ptr, unsigned char handle[64]);
+int pf_ipc_open(const unsigned char handle[64], void** ptr);
+int pf_ipc_close(void* ptr);
 /* let kernels of the CURRENT device store into memory of `peer_device` (cudaDeviceEnablePeerAccess; idempotent) — needed once
  * per peer before pf_allgather_views pushes into IPC-mapped buffers that live on the other GPUs of the node */
 int pf_enable_peer_access(int peer_device);

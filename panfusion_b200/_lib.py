@@ -51,6 +51,7 @@ class FmhaArgs(C.Structure):
         ("q_bstride", C.c_int64), ("k_bstride", C.c_int64), ("v_bstride", C.c_int64),
         ("scale", C.c_float), ("bias", C.c_void_p), ("bias_bstride", C.c_int64), ("bias_ld", C.c_int32),
         ("bias_flags", C.c_void_p), ("flags_bstride", C.c_int64), ("flags_ld", C.c_int32),
+        ("bias_tile_off", C.c_void_p),
     ]
 
 
@@ -78,11 +79,12 @@ EXPORTS = [
     "pf_last_error", "pf_version", "pf_check_device",
     "pf_e2p", "pf_e2p_shared", "pf_e2p_py360", "pf_p2e",
     "pf_gemm_taps", "pf_gemm_pick_block_n", "pf_gemm_splitk_plan", "pf_gemm_row_stats_slots",
-    "pf_fmha_fwd", "pf_bias_tile_flags",
+    "pf_fmha_fwd", "pf_bias_tile_flags", "pf_bias_tile_scan", "pf_bias_tile_pack",
     "pf_groupnorm_ws_floats", "pf_groupnorm_stats", "pf_conv_prep", "pf_gn_prep_ws_floats", "pf_gn_prep", "pf_layernorm",
     "pf_conv_in", "pf_conv_out", "pf_copy2d", "pf_pad_pano", "pf_softmax_rows", "pf_tensor_to_image", "pf_timestep_embed", "pf_cfg_ddim_step", "pf_cfg_ddim_step_dev",
     "pf_eppa_tables", "pf_eppa_pe",
-    "pf_allgather_views", "pf_enable_peer_access", "pf_embed_tokens",
+    "pf_allgather_views", "pf_enable_peer_access", "pf_comm_alloc", "pf_comm_free", "pf_ipc_export", "pf_ipc_open",
+    "pf_ipc_close", "pf_embed_tokens",
 ]
 
 

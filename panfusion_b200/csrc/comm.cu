@@ -13,6 +13,8 @@
 // advanced by the kernel itself, so a replayed graph keeps working. A buffer is only rewritten one whole step later, and
 // a rank can never be more than one collective ahead of a peer (each collective is also a barrier), so per-site buffers
 // need no further flow control.
+#include <string.h>
+
 #include "pf_common.cuh"
 
 namespace pf {
@@ -77,6 +79,49 @@ __global__ void __launch_bounds__(256) allgather_push_wait_kernel(const AllGathe
 }
 
 }  // namespace pf
+
+// ---- receive-buffer plumbing: plain cudaMalloc memory exported / imported with CUDA IPC -------------------------------------
+// (the caller's PyTorch allocator is not involved: an IPC handle names a whole cudaMalloc allocation, and the importing side
+// must open it on ITS device with lazy peer access, which is how NCCL's P2P transport maps peer buffers too)
+extern "C" int pf_comm_alloc(long long bytes, void** ptr) {
+  using namespace pf;
+  PF_CHECK_ARG(bytes > 0 && ptr, "pf_comm_alloc: bad arguments");
+  void* p = nullptr;
+  if (int rc = check_cuda(cudaMalloc(&p, (size_t)bytes), "cudaMalloc(comm buffer)")) return rc;
+  if (int rc = check_cuda(cudaMemset(p, 0, (size_t)bytes), "cudaMemset(comm buffer)")) return rc;
+  if (int rc = check_cuda(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return rc;
+  *ptr = p;
+  return PF_OK;
+}
+
+extern "C" int pf_comm_free(void* ptr) {
+  return pf::check_cuda(cudaFree(ptr), "cudaFree(comm buffer)");
+}
+
+extern "C" int pf_ipc_export(const void* ptr, unsigned char handle[64]) {
+  using namespace pf;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  PF_CHECK_ARG(ptr && handle, "pf_ipc_export: null pointer");
+  cudaIpcMemHandle_t h;
+  if (int rc = check_cuda(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)), "cudaIpcGetMemHandle")) return rc;
+  memcpy(handle, &h, 64);
+  return PF_OK;
+}
+
+extern "C" int pf_ipc_open(const unsigned char handle[64], void** ptr) {
+  using namespace pf;
+  PF_CHECK_ARG(ptr && handle, "pf_ipc_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* p = nullptr;
+  if (int rc = check_cuda(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return rc;
+  *ptr = p;
+  return PF_OK;
+}
+
+extern "C" int pf_ipc_close(void* ptr) {
+  return pf::check_cuda(cudaIpcCloseMemHandle(ptr), "cudaIpcCloseMemHandle");
+}
 
 extern "C" int pf_enable_peer_access(int peer_device) {
   using namespace pf;

@@ -43,6 +43,9 @@ struct FmhaParams {
   const uint8_t* bias_flags;
   long long flags_bstride;
   int flags_ld;
+  // tile-packed bias (pf_bias_tile_pack): tile_off[bias batch][ceil(Lq/128)][ceil(Lk/64)] = index of the 128x64 tile in
+  // `bias` (then a [n_live][128][64] store) or -1 for an all -1 tile; replaces bias_ld / bias_flags addressing
+  const int* tile_off;
 };
 
 // ex2.approx.ftz: one MUFU op (exp2f() adds denormal / range fix-up instructions we do not need: inputs are <= 0)
@@ -214,10 +217,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float m_used = -INFINITY, l_run = 0.f;
     const float* bias_row = nullptr;
     const uint8_t* flag_row = nullptr;
+    const int* off_row = nullptr;
     if constexpr (HAS_BIAS) {
       const int qq = q < p.Lq ? q : p.Lq - 1;
-      bias_row = p.bias + (long long)b * p.bias_bstride + (long long)qq * p.bias_ld;
-      if (p.bias_flags) flag_row = p.bias_flags + (long long)b * p.flags_bstride + (long long)qt * p.flags_ld;
+      if (p.tile_off) {
+        off_row = p.tile_off + (long long)b * p.flags_bstride + (long long)qt * p.flags_ld;
+        bias_row = p.bias + row * FA_BLOCK_N;  // + tile index * 128 * 64 per key tile
+      } else {
+        bias_row = p.bias + (long long)b * p.bias_bstride + (long long)qq * p.bias_ld;
+        if (p.bias_flags) flag_row = p.bias_flags + (long long)b * p.flags_bstride + (long long)qt * p.flags_ld;
+      }
     }
     const float sc = HAS_BIAS ? 1.0f : p.scale_log2;
 
@@ -242,12 +251,15 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // sv <- logits in log2 units. Without bias the softmax scale is folded into the exp2 argument below (one FFMA
       // per element); with bias: t = s*scale*log2e + bias*log2e.
       if constexpr (HAS_BIAS) {
-        const bool constant_tile = flag_row != nullptr && flag_row[j] != 0;
+        const int toff = off_row ? off_row[j] : 0;
+        const bool constant_tile = off_row ? toff < 0 : (flag_row != nullptr && flag_row[j] != 0);
         if (constant_tile) {
 #pragma unroll
           for (int e = 0; e < FA_BLOCK_N; ++e) sv[e] = fmaf(sv[e], p.scale_log2, -LOG2E);
-        } else if (k0 + FA_BLOCK_N <= p.Lk) {
-          const float4* b4 = reinterpret_cast<const float4*>(bias_row + k0);
+        } else if (off_row || k0 + FA_BLOCK_N <= p.Lk) {
+          // packed tiles are always full 64-wide rows (zero beyond Lk: those keys are masked below)
+          const float4* b4 = off_row ? reinterpret_cast<const float4*>(bias_row + (long long)toff * (FA_BLOCK_M * FA_BLOCK_N))
+                                     : reinterpret_cast<const float4*>(bias_row + k0);
 #pragma unroll
           for (int e = 0; e < FA_BLOCK_N / 4; ++e) {
             const float4 t = __ldg(b4 + e);
@@ -382,6 +394,7 @@ static int launch_fmha(const pf_fmha_args* a, cudaStream_t st) {
   p.out = a->out; p.out_ld = a->out_ld;
   p.bias = a->bias; p.bias_bstride = a->bias_bstride; p.bias_ld = a->bias_ld;
   p.bias_flags = a->bias_flags; p.flags_bstride = a->flags_bstride; p.flags_ld = a->flags_ld;
+  p.tile_off = a->bias_tile_off;
   auto kern = fmha_fwd_kernel<D, BF16, HAS_BIAS>;
   constexpr int SMEM = fmha_smem_bytes<D>();
   static bool attr_set = false;
@@ -411,8 +424,10 @@ extern "C" int pf_fmha_fwd(const pf_fmha_args* a, void* stream) {
   PF_CHECK_ARG(((uintptr_t)a->q & 15) == 0 && ((uintptr_t)a->k & 15) == 0 && ((uintptr_t)a->v & 15) == 0 &&
                    ((uintptr_t)a->out & 15) == 0,
                "pf_fmha_fwd: operands must be 16-byte aligned");
-  PF_CHECK_ARG(!a->bias || (a->bias_ld % 4 == 0 && ((uintptr_t)a->bias & 15) == 0 && a->bias_ld >= a->Lk),
+  PF_CHECK_ARG(!a->bias || a->bias_tile_off || (a->bias_ld % 4 == 0 && ((uintptr_t)a->bias & 15) == 0 && a->bias_ld >= a->Lk),
                "pf_fmha_fwd: bias must be 16-byte aligned with bias_ld %% 4 == 0");
+  PF_CHECK_ARG(!a->bias_tile_off || (a->bias && ((uintptr_t)a->bias & 15) == 0 && !a->bias_flags && a->flags_ld > 0),
+               "pf_fmha_fwd: a tile-packed bias needs the packed store in `bias`, flags_ld = tiles per row, no bias_flags");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool bf = a->dtype == PF_BF16;
   const bool hb = a->bias != nullptr;

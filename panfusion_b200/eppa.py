@@ -64,6 +64,10 @@ class _SphericalPE(nn.Module):  # transformer.py:165-183: only the frequency tab
         self.register_buffer("freq_bands", base ** torch.linspace(0, n_freqs - 1, n_freqs))
 
 
+# resident form of the correspondence bias: tile-packed (only non-constant 128 x 64 tiles) unless PF_EPPA_DENSE_BIAS=1
+PACK_BIAS = __import__("os").environ.get("PF_EPPA_DENSE_BIAS", "0") == "0"
+
+
 class CameraTables:
     """Per (camera set, level) cache of the EPPA bias tables and per (.., freq table) PE tables. The +90 degree
     rotation per step (PanFusion.py:114-123) cycles through a handful of camera sets, and the two CFG halves carry
@@ -100,10 +104,18 @@ class CameraTables:
         """Every cached tensor that belongs to camera set `key` (to be held by whoever captured their addresses)."""
         key = self.dedup_any(key)
         out = []
+
+        def collect(v):
+            if torch.is_tensor(v):
+                out.append(v)
+            elif isinstance(v, (tuple, list)):
+                for t in v:
+                    collect(t)
+
         for cache in (self._bias, self._pe, self._rec):
             for k, v in cache.items():
                 if self._key_of(k) in key:
-                    out.extend(t for t in (v if isinstance(v, (tuple, list)) else (v,)) if torch.is_tensor(t))
+                    collect(v)
         return out
 
     @staticmethod
@@ -153,8 +165,14 @@ class CameraTables:
             V = len(key[0])
             ce, cp = self._records(key, V, ph, pw, dev)
             b1, b2 = ops.eppa_tables(ce, cp, V // groups, ph, pw, eh, ew)
-            # block-sparsity hints: most (query tile, key tile) pairs have no geometric correspondence at all
-            self._bias[k] = (b1, b2, ops.bias_tile_flags(b1), ops.bias_tile_flags(b2))
+            # Most (query tile, key tile) pairs have no geometric correspondence at all: the resident form keeps only the
+            # ~15 % of 128 x 64 tiles that are not entirely -1 ("packed": store + tile index table). A direction whose
+            # per-view query count is not a multiple of the 128-row tile (the 8x8 level) cannot be sliced by view shard and
+            # stays dense (it is tiny).
+            P, E = ph * pw, eh * ew
+            d1 = ("packed", *ops.bias_pack_tiles(b1)) if (PACK_BIAS and E % 128 == 0) else ("dense", b1, ops.bias_tile_flags(b1))
+            d2 = ("packed", *ops.bias_pack_tiles(b2)) if (PACK_BIAS and P % 128 == 0) else ("dense", b2, ops.bias_tile_flags(b2))
+            self._bias[k] = (d1, d2)
         return self._bias[k]
 
     def pe(self, key, ph, pw, eh, ew, freq_bands: Tensor, dev):
@@ -213,15 +231,24 @@ class WarpAttn(nn.Module):
         ph, pw, eh, ew = pers.H, pers.W, equi.H, equi.W
         P, E = ph * pw, eh * ew
         key, groups = CameraTables.dedup(cam_key, b)
-        bias1, bias2, flags1, flags2 = self.tables.bias(key, groups, ph, pw, eh, ew, dev)  # [G, E, m*P], [G, m*P, E]
+        d1, d2 = self.tables.bias(key, groups, ph, pw, eh, ew, dev)  # direction 1 [G, E, m*P], direction 2 [G, m*P, E]
         pers_pe, equi_pe = self.tables.pe(key, ph, pw, eh, ew, self.pe.freq_bands, dev)  # [G*m*P, C], [E, C]
+        kw1 = dict(bias_tiles=(d1[1], d1[2])) if d1[0] == "packed" else dict(bias=d1[1], bias_flags=d1[2])
         if m_loc != m:
-            bias2 = bias2[:, v0 * P:(v0 + m_loc) * P]
-            # flag rows are 128-query tiles: usable for the local slice only when it starts on a tile boundary
-            flags2 = flags2[:, (v0 * P) // 128:((v0 + m_loc) * P + 127) // 128].contiguous() \
-                if (v0 * P) % 128 == 0 and (m_loc * P) % 128 == 0 else None
+            # this rank's views = a contiguous range of direction 2's query rows
+            if d2[0] == "packed":
+                off2 = d2[2][:, (v0 * P) // 128:((v0 + m_loc) * P) // 128].contiguous()
+                kw2 = dict(bias_tiles=(d2[1], off2))
+            else:
+                bias2 = d2[1][:, v0 * P:(v0 + m_loc) * P]
+                # flag rows are 128-query tiles: usable for the local slice only when it starts on a tile boundary
+                flags2 = d2[2][:, (v0 * P) // 128:((v0 + m_loc) * P + 127) // 128].contiguous() \
+                    if (v0 * P) % 128 == 0 and (m_loc * P) % 128 == 0 else None
+                kw2 = dict(bias=bias2, bias_flags=flags2)
             pers_pe = pers_pe.reshape(groups, m * P, C)[:, v0 * P:(v0 + m_loc) * P].reshape(groups * m_loc * P, C)
             pers_pe = pers_pe if pers_pe.is_contiguous() else self._local_pe(pers_pe, (key, ph, pw, v0, m_loc))
+        else:
+            kw2 = dict(bias_tiles=(d2[1], d2[2])) if d2[0] == "packed" else dict(bias=d2[1], bias_flags=d2[2])
         heads, d = w["heads"], C // w["heads"]
         Tp, Te = b * m_loc * P, b * E
         new = lambda rows, n: torch.empty((rows, n), dtype=dt, device=dev)
@@ -270,13 +297,11 @@ class WarpAttn(nn.Module):
         # direction 1 (modules.py:44-48): pano pixels query every view's pixels
         with torch.cuda.stream(side if two else main):
             o1 = torch.empty((b, E, C), dtype=dt, device=dev)
-            ops.fmha(qkv_e[..., :C], k_all, v_all, o1, heads=heads, head_dim=d, scale=scale, bias=bias1,
-                     bias_flags=flags1)
+            ops.fmha(qkv_e[..., :C], k_all, v_all, o1, heads=heads, head_dim=d, scale=scale, **kw1)
             equi_out = finish(o1.reshape(Te, C), equi.t, Te)
         # direction 2 (modules.py:51-55): view pixels query the pano; reads the INPUT features
         o2 = torch.empty((b, m_loc * P, C), dtype=dt, device=dev)
-        ops.fmha(qkv_p[..., :C], qkv_e[..., C:2 * C], qkv_e[..., 2 * C:], o2, heads=heads, head_dim=d, scale=scale,
-                 bias=bias2, bias_flags=flags2)
+        ops.fmha(qkv_p[..., :C], qkv_e[..., C:2 * C], qkv_e[..., 2 * C:], o2, heads=heads, head_dim=d, scale=scale, **kw2)
         pers_out = finish(o2.reshape(Tp, C), pers.t, Tp)
         return Img(pers_out, b * m_loc, ph, pw), Img(equi_out, b, eh, ew)
 

@@ -138,8 +138,27 @@ def bias_tile_flags(bias: Tensor) -> Tensor:
     return flags
 
 
+def bias_pack_tiles(bias: Tensor):
+    """Dense fp32 bias [G, Lq, Lk] -> (store [n_live, 128, 64] fp32, tile_off int32 [G, ceil(Lq/128), ceil(Lk/64)]): only the
+    128 x 64 tiles that are not entirely -1 are kept (pf_bias_tile_flags -> pf_bias_tile_scan -> pf_bias_tile_pack)."""
+    assert bias.dtype == torch.float32 and bias.dim() == 3 and bias.stride(2) == 1
+    G, Lq, Lk = bias.shape
+    flags = bias_tile_flags(bias)
+    tile_off = torch.empty(flags.shape, dtype=torch.int32, device=bias.device)
+    n_live = torch.empty(1, dtype=torch.int32, device=bias.device)
+    lib = _lib.lib()
+    _count(1)
+    _lib.check(lib.pf_bias_tile_scan(_vp(flags), flags.numel(), _vp(tile_off), _vp(n_live), _st()))
+    n = int(n_live.item())  # host sync: table construction is a one-off per camera set
+    store = torch.empty((max(n, 1), 128, 64), dtype=torch.float32, device=bias.device)
+    _count(1)
+    _lib.check(lib.pf_bias_tile_pack(_vp(bias), G, Lq, Lk, bias.stride(1), C.c_int64(bias.stride(0)), _vp(tile_off),
+                                     _vp(store), _st()))
+    return store, tile_off
+
+
 def fmha(q: Tensor, k: Tensor, v: Tensor, out: Tensor, *, heads: int, head_dim: int, scale: float,
-         bias: Optional[Tensor] = None, bias_flags: Optional[Tensor] = None) -> Tensor:
+         bias: Optional[Tensor] = None, bias_flags: Optional[Tensor] = None, bias_tiles: Optional[tuple] = None) -> Tensor:
     """out[b, l, h*d:(h+1)*d] = softmax(q_h k_h^T * scale + bias) v_h; see pf_fmha_fwd.
 
     q: [B, Lq, >=H*d] view (last stride 1), k/v: [B, Lk, >=H*d] views — slices of a fused QKV buffer are fine.
@@ -158,6 +177,14 @@ def fmha(q: Tensor, k: Tensor, v: Tensor, out: Tensor, *, heads: int, head_dim: 
     a.q_bstride, a.k_bstride, a.v_bstride = q.stride(0), k.stride(0), v.stride(0)
     assert out.stride(0) == Lq * out.stride(1)
     a.scale = float(scale)
+    if bias_tiles is not None:
+        store, tile_off = bias_tiles  # tile-packed bias: store [n, 128, 64] fp32, tile_off int32 [G, QT, KT] (G = 1: shared)
+        assert bias is None and store.dtype == torch.float32 and store.is_contiguous() and tile_off.dtype == torch.int32
+        assert tile_off.dim() == 3 and tile_off.is_contiguous()
+        assert tile_off.shape[1] == (Lq + 127) // 128 and tile_off.shape[2] == (Lk + 63) // 64 and tile_off.shape[0] in (1, B)
+        a.bias, a.bias_tile_off = store.data_ptr(), tile_off.data_ptr()
+        a.flags_ld = tile_off.stride(1)
+        a.flags_bstride = tile_off.stride(0) if tile_off.shape[0] > 1 else 0
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.stride(-1) == 1
         a.bias = bias.data_ptr()

@@ -32,17 +32,28 @@ DEVICE_GATHER = __import__("os").environ.get("PF_DEVICE_GATHER", "1") != "0"
 
 
 class _Site:
-    __slots__ = ("recv", "ctrl", "peer_data", "peer_flags", "keep")
+    __slots__ = ("recv", "ctrl_ptr", "peer_data", "peer_flags", "base", "opened")
+
+
+class _RawCuda:
+    """Zero-copy torch view of a raw device allocation (through __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(ptr, False), version=3)
+
+
+_TYPESTR = {torch.float32: "<f4", torch.float16: "<f2", torch.bfloat16: "<u2", torch.int32: "<i4", torch.uint8: "|u1"}
 
 
 class DeviceAllGather:
     """All-gather inside `group` through IPC-mapped receive buffers and the `pf_allgather_views` kernel.
 
-    A call site is identified by `key` (slot, index of the collective inside the step, shape): its buffers are created on
-    first use — an eager, host-synchronising exchange of IPC handles, so the first step of every slot must run eagerly
-    (the sampler's warm-up step does) — and reused afterwards. `slot` separates the buffers of consecutive steps: a site
-    is rewritten only after every peer has passed at least one later collective of the SAME slot sequence (see
-    csrc/comm.cu), which the sampler guarantees by cycling through >= 2 slots."""
+    A call site is identified by `key` (slot, index of the collective inside the step, shape): its buffer — cudaMalloc'ed
+    by the library, [S slices | S flag words | 2 state words] — is created on first use with an eager, host-synchronising
+    exchange of CUDA IPC handles, so the first step of every slot must run eagerly (the sampler's warm-up step does), and
+    reused afterwards. `slot` separates the buffers of consecutive steps: a site is rewritten only after every peer has
+    passed at least one later collective of the SAME slot sequence (see csrc/comm.cu), which the sampler guarantees by
+    cycling through >= 2 slots."""
 
     def __init__(self, group):
         self.group = group
@@ -52,29 +63,37 @@ class DeviceAllGather:
 
     def _create(self, key, x: Tensor) -> _Site:
         import ctypes as C
+        from . import _lib
+        lib = _lib.lib()
         S = self.S
+        nbytes = x.numel() * x.element_size()
+        data_bytes = (S * nbytes + 255) // 256 * 256
         site = _Site()
-        site.recv = torch.empty((S, *x.shape), dtype=x.dtype, device=x.device)
-        site.ctrl = torch.zeros(64, dtype=torch.int32, device=x.device)  # [0:S) flags, [S], [S+1] epoch / CTA counter
-        torch.cuda.synchronize()
-        mine = [t.untyped_storage()._share_cuda_() for t in (site.recv, site.ctrl)]
-        offs = [site.recv.storage_offset() * site.recv.element_size(), site.ctrl.storage_offset() * 4]
+        base = C.c_void_p()
+        _lib.check(lib.pf_comm_alloc(C.c_longlong(data_bytes + 256), C.byref(base)))
+        site.base = base.value
+        site.ctrl_ptr = site.base + data_bytes
+        handle = (C.c_ubyte * 64)()
+        _lib.check(lib.pf_ipc_export(C.c_void_p(site.base), handle))
         everyone = [None] * S
-        dist.all_gather_object(everyone, (mine, offs), group=self.group)
-        data_ptrs, flag_ptrs, site.keep = [], [], []
-        for r, (handles, off) in enumerate(everyone):
+        dist.all_gather_object(everyone, bytes(handle), group=self.group)
+        data_ptrs, flag_ptrs, site.opened = [], [], []
+        for r, h in enumerate(everyone):
             if r == self.rank:
-                data_ptrs.append(site.recv.data_ptr())
-                flag_ptrs.append(site.ctrl.data_ptr())
-                continue
-            from . import _lib
-            _lib.check(_lib.lib().pf_enable_peer_access(int(handles[0][0])))  # this GPU's kernels store into that GPU
-            st = [torch.UntypedStorage._new_shared_cuda(*h) for h in handles]
-            site.keep.append(st)  # the mappings live as long as the site
-            data_ptrs.append(st[0].data_ptr() + off[0])
-            flag_ptrs.append(st[1].data_ptr() + off[1])
+                peer = site.base
+            else:
+                out = C.c_void_p()
+                _lib.check(lib.pf_ipc_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(out)))
+                peer = out.value
+                site.opened.append(peer)
+            data_ptrs.append(peer)
+            flag_ptrs.append(peer + data_bytes)
         site.peer_data = torch.tensor(data_ptrs, dtype=torch.int64, device=x.device)
         site.peer_flags = torch.tensor(flag_ptrs, dtype=torch.int64, device=x.device)
+        if x.dtype not in _TYPESTR:
+            raise TypeError(f"DeviceAllGather: unsupported dtype {x.dtype}")
+        raw = torch.as_tensor(_RawCuda(site.base, (S * x.numel(),), _TYPESTR[x.dtype]), device=x.device)
+        site.recv = (raw.view(torch.bfloat16) if x.dtype == torch.bfloat16 else raw).view(S, *x.shape)
         torch.cuda.synchronize()
         dist.barrier(group=self.group)  # every rank's flag words are zeroed and mapped before anyone pushes
         self.sites[key] = site
@@ -93,7 +112,7 @@ class DeviceAllGather:
                                    "(run one eager step first)")
             site = self._create(key, x)
         nbytes = x.numel() * x.element_size()
-        ctrl = site.ctrl.data_ptr()
+        ctrl = site.ctrl_ptr
         ops._count(1)
         _lib.check(_lib.lib().pf_allgather_views(
             C.c_void_p(x.data_ptr()), C.c_longlong(nbytes), C.c_void_p(site.peer_data.data_ptr()),

@@ -98,3 +98,40 @@ def test_bias_tile_flags_and_sparse_bias_attention(cuda_device):
     ops.fmha(q, k, v, o2, heads=H, head_dim=d, scale=d ** -0.5, bias=bias, bias_flags=flags)
     torch.testing.assert_close(o1.float(), o2.float(), rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(o2.float(), _ref(q, k, v, H, d, d ** -0.5, bias), rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("Lq,Lk,G", [(2048, 8192, 1), (512, 2048, 2), (300, 200, 1), (128, 64, 1)])
+def test_tile_packed_bias_equals_dense(cuda_device, Lq, Lk, G):
+    """The resident (tile-packed) form of the EPPA bias — only the 128 x 64 tiles that are not entirely -1, plus a tile index
+    table — must give exactly the attention output of the dense table (models/modules/transformer.py:57-74 with the mask of
+    :68), including ragged edge tiles and per-batch tables."""
+    from panfusion_b200 import ops
+    B, H, d = max(G, 2) if G > 1 else 2, 3, 32
+    B = G if G > 1 else 2
+    g = torch.Generator().manual_seed(Lq + Lk)
+    bias = torch.full((G, Lq, Lk), -1.0)
+    # sparse structure like the correspondence bias: a band of non-constant entries per query row
+    for gi in range(G):
+        for r in range(0, Lq, 7):
+            c0 = (r * 37 + gi * 11) % max(1, Lk - 40)
+            bias[gi, r:r + 7, c0:c0 + 40] = torch.rand(min(7, Lq - r), min(40, Lk - c0), generator=g) * 2 - 1
+    bias = bias.to(cuda_device)
+    store, off = ops.bias_pack_tiles(bias)
+    live = int((off >= 0).sum())
+    assert store.shape[0] == max(live, 1) and live < off.numel() or Lq <= 300
+    # every live tile reproduces the dense tile (zero padding outside), every dropped tile was all -1
+    for (gi, qt, kt) in [(0, 0, 0), (G - 1, off.shape[1] - 1, off.shape[2] - 1)]:
+        o = int(off[gi, qt, kt])
+        dense = bias[gi, qt * 128:(qt + 1) * 128, kt * 64:(kt + 1) * 64]
+        if o < 0:
+            assert bool((dense == -1).all())
+        else:
+            assert torch.equal(store[o, :dense.shape[0], :dense.shape[1]], dense)
+    q = torch.randn(B, Lq, H * d, generator=g).bfloat16().to(cuda_device)
+    k = torch.randn(B, Lk, H * d, generator=g).bfloat16().to(cuda_device)
+    v = torch.randn(B, Lk, H * d, generator=g).bfloat16().to(cuda_device)
+    o_dense = torch.empty_like(q)
+    o_pack = torch.empty_like(q)
+    ops.fmha(q, k, v, o_dense, heads=H, head_dim=d, scale=d ** -0.5, bias=bias, bias_flags=ops.bias_tile_flags(bias))
+    ops.fmha(q, k, v, o_pack, heads=H, head_dim=d, scale=d ** -0.5, bias_tiles=(store, off))
+    assert torch.equal(o_dense, o_pack)

@@ -11,6 +11,19 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_device_allgather_matches_nccl(world):
+    """pf_allgather_views (push over NVLink into IPC-mapped buffers, flag handshake) == ncclAllGather, eager and as a
+    replayed CUDA graph (scripts/allgather_check.py)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29700 + world), str(ROOT / "scripts" / "allgather_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MISMATCH" not in r.stdout and "OK" in r.stdout
+
+
 @pytest.mark.parametrize("split_k", ["0", "1"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_matches_single(world, split_k):
@@ -23,16 +36,3 @@ def test_sharded_matches_single(world, split_k):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env={**os.environ, "PF_SPLIT_K": split_k})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MISMATCH" not in r.stdout
-
-
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_device_allgather_matches_nccl(world):
-    """pf_allgather_views (push over NVLink into IPC-mapped buffers, flag handshake) == ncclAllGather, eager and as a
-    replayed CUDA graph (scripts/allgather_check.py)."""
-    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(29700 + world), str(ROOT / "scripts" / "allgather_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "MISMATCH" not in r.stdout and "OK" in r.stdout

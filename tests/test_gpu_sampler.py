@@ -150,9 +150,9 @@ def test_camera_table_cache_is_bounded(cuda_device):
     from panfusion_b200.eppa import CameraTables
     tabs = CameraTables(max_camera_sets=2)
     rigs = [tuple((tuple([90.0] * 2), tuple([float(t), float(t) + 180.0]), tuple([0.0, 0.0]))) for t in (0, 30, 60)]
-    first = [tabs.bias(r, 1, 8, 8, 8, 16, cuda_device)[0].clone() for r in rigs]
+    first = [tabs.bias(r, 1, 8, 8, 8, 16, cuda_device)[0][1].clone() for r in rigs]
     assert len(tabs._lru) == 2 and rigs[0] not in tabs._lru
     assert all(tabs._key_of(k) in tabs._lru for cache in (tabs._bias, tabs._rec) for k in cache)
-    again = tabs.bias(rigs[0], 1, 8, 8, 8, 16, cuda_device)[0]
+    again = tabs.bias(rigs[0], 1, 8, 8, 8, 16, cuda_device)[0][1]
     assert torch.equal(again, first[0]) and rigs[1] not in tabs._lru
     assert len(tabs.tensors_of(rigs[0])) >= 4
