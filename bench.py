@@ -296,6 +296,7 @@ def run_b200(args):
                        "l2": "working set (3.4 GB weights + activations per step) exceeds the 126 MB L2; no flush needed"},
             "clocks": clk.summary(),
             "e2e": {"value": round(e2e_sps, 4), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "eppa_tables_mb": round(model.cp_blocks_mid.tables.nbytes() / 2 ** 20, 1),  # all 4 rotation phases, resident form
             "gpu_launches": int(launches_per_step * args.steps) if launches_per_step else int(ops.LAUNCHES - l0),
             "launches_per_step": launches_per_step,
             "roofline": {"bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf_sust"], "unit": "TFLOP/s",

@@ -128,6 +128,25 @@ class CameraTables:
                 keys.add(CameraTables.dedup(key, b)[0])
         return tuple(keys)
 
+    def nbytes(self) -> int:
+        """Device bytes held by the cache (bias tables in their resident form, PE tables, camera records)."""
+        seen, total = set(), 0
+
+        def walk(v):
+            nonlocal total
+            if torch.is_tensor(v):
+                if v.data_ptr() not in seen:
+                    seen.add(v.data_ptr())
+                    total += v.numel() * v.element_size()
+            elif isinstance(v, (tuple, list)):
+                for t in v:
+                    walk(t)
+
+        for cache in (self._bias, self._pe, self._rec):
+            for v in cache.values():
+                walk(v)
+        return total
+
     def clear(self) -> None:
         self._bias.clear()
         self._pe.clear()
