@@ -313,17 +313,27 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         l_run *= alpha;
         m_used = m_new;
       }
-      float ps[4] = {0.f, 0.f, 0.f, 0.f};
+      // exp2(s * scale - m) for two neighbouring keys per FFMA2, row sums on FADD2 (packed fp32x2, sm_100): the softmax
+      // warps share their issue slots with the MUFU pipe that bounds this kernel, so every FMA-pipe instruction saved counts
+      f32x2 ps2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ps2[i] = pack_f2(0.f, 0.f);
+      const f32x2 sc2 = pack_f2(sc, sc), nm2 = pack_f2(-m_used, -m_used);
       uint32_t pk[FA_BLOCK_N / 2];
 #pragma unroll
       for (int e = 0; e < FA_BLOCK_N; e += 2) {
-        const float p0 = fast_exp2(fmaf(sv[e], sc, -m_used));
-        const float a1 = fmaf(sv[e + 1], sc, -m_used);
+        float a0, a1;
+        unpack_f2(fma_f2(pack_f2(sv[e], sv[e + 1]), sc2, nm2), a0, a1);
+        const float p0 = fast_exp2(a0);
         const float p1 = (FA_POLY_EXP && ((e >> 1) & 1)) ? poly_exp2(a1) : fast_exp2(a1);
-        ps[(e >> 1) & 3] += p0 + p1;
+        ps2[(e >> 1) & 3] = add_f2(ps2[(e >> 1) & 3], pack_f2(p0, p1));
         pk[e >> 1] = FA_ALU_PACK ? pack_prob<BF16>(p0, p1) : pack2<BF16>(p0, p1);
       }
-      l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+      {
+        float lo, hi;
+        unpack_f2(add_f2(add_f2(ps2[0], ps2[1]), add_f2(ps2[2], ps2[3])), lo, hi);
+        l_run += lo + hi;
+      }
       if (j > 0 && !o_waited) {
         mbar_wait(o_done, (j - 1) & 1);  // the tensor core is done reading sP (tile j-1)
         tc_fence_after();
