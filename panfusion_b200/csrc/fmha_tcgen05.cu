@@ -11,6 +11,8 @@
 // P goes registers -> swizzled smem (K-major A operand), P V lands in a TMEM scratch tile that the softmax
 // threads fold into their fp32 register accumulator with the online-softmax rescale.
 // 192 threads: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2..5 softmax / epilogue.
+#include <stdlib.h>
+
 #include "pf_common.cuh"
 
 namespace pf {
@@ -26,6 +28,9 @@ constexpr int FA_THREADS = 192;
 #endif
 #ifndef PF_FA_ALU_PACK
 #define PF_FA_ALU_PACK 0
+#endif
+#ifndef PF_FA_POLY_DEFAULT
+#define PF_FA_POLY_DEFAULT 0
 #endif
 constexpr bool FA_POLY_EXP = PF_FA_POLY_EXP != 0;
 constexpr bool FA_ALU_PACK = PF_FA_ALU_PACK != 0;
@@ -68,6 +73,25 @@ __device__ __forceinline__ float poly_exp2(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// exp2 of two values at once on the FMA / ALU pipes (same Cody-Waite split and cubic as poly_exp2): 2 FMNMX + 2 FADD2 +
+// 4 FFMA2 + 2 LEA = 10 issue slots for two exponentials and NO MUFU cycles (an ex2 occupies the quarter-rate XU pipe for 8
+// cycles per warp). Used for a fixed fraction of the key pairs of every tile (POLY_PAIRS of 8) to balance XU against issue.
+__device__ __forceinline__ void poly_exp2_pair(float x0, float x1, float& y0, float& y1) {
+  const f32x2 x = pack_f2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const f32x2 magic = pack_f2(12582912.0f, 12582912.0f);
+  const f32x2 t = add_f2(x, magic);
+  const f32x2 r = add_f2(t, pack_f2(-12582912.0f, -12582912.0f));
+  const f32x2 f = fma_f2(r, pack_f2(-1.0f, -1.0f), x);
+  f32x2 p = fma_f2(f, pack_f2(0.05517164f, 0.05517164f), pack_f2(0.24261112f, 0.24261112f));
+  p = fma_f2(p, f, pack_f2(0.69326099f, 0.69326099f));
+  p = fma_f2(p, f, pack_f2(0.99992807f, 0.99992807f));
+  float p0, p1, t0, t1;
+  unpack_f2(p, p0, p1);
+  unpack_f2(t, t0, t1);
+  y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
 // two non-negative fp32 -> packed bf16x2 by integer rounding (half-up; ties differ from RNE by 1 ulp with
 // probability 2^-16). cvt.rn.bf16x2.f32 issues on the XU pipe next to the exponentials; this stays on the ALU.
 __device__ __forceinline__ uint32_t pack_bf16_alu(float a, float b) {
@@ -94,7 +118,7 @@ __host__ __device__ constexpr int fmha_smem_bytes() {
 // becomes a rare event instead of per-tile work. Without a per-thread fp32 O accumulator the kernel fits three CTAs
 // per SM (112 registers, 64 KB smem, 128 TMEM columns each): three softmax warps per scheduler hide the
 // exp / TMEM / barrier latencies of one another.
-template <int D, bool BF16, bool HAS_BIAS>
+template <int D, bool BF16, bool HAS_BIAS, int POLY_PAIRS>
 __global__ void __launch_bounds__(FA_THREADS, 3)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
@@ -324,8 +348,13 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int e = 0; e < FA_BLOCK_N; e += 2) {
         float a0, a1;
         unpack_f2(fma_f2(pack_f2(sv[e], sv[e + 1]), sc2, nm2), a0, a1);
-        const float p0 = fast_exp2(a0);
-        const float p1 = (FA_POLY_EXP && ((e >> 1) & 1)) ? poly_exp2(a1) : fast_exp2(a1);
+        float p0, p1;
+        if (((e >> 1) & 7) < POLY_PAIRS) {  // compile-time after unrolling: this pair's exponentials skip the MUFU
+          poly_exp2_pair(a0, a1, p0, p1);
+        } else {
+          p0 = fast_exp2(a0);
+          p1 = (FA_POLY_EXP && ((e >> 1) & 1)) ? poly_exp2(a1) : fast_exp2(a1);
+        }
         ps2[(e >> 1) & 3] = add_f2(ps2[(e >> 1) & 3], pack_f2(p0, p1));
         pk[e >> 1] = FA_ALU_PACK ? pack_prob<BF16>(p0, p1) : pack2<BF16>(p0, p1);
       }
@@ -391,7 +420,7 @@ static int make_qkv_tmap(CUtensorMap* tm, int dtype, const void* ptr, int B, int
   return make_tmap(tm, dtype, 4, ptr, dims, str, box, D == 64 ? 128 : 64);
 }
 
-template <int D, bool BF16, bool HAS_BIAS>
+template <int D, bool BF16, bool HAS_BIAS, int POLY_PAIRS>
 static int launch_fmha(const pf_fmha_args* a, cudaStream_t st) {
   CUtensorMap tmQ, tmK, tmV;
   int rc;
@@ -405,7 +434,7 @@ static int launch_fmha(const pf_fmha_args* a, cudaStream_t st) {
   p.bias = a->bias; p.bias_bstride = a->bias_bstride; p.bias_ld = a->bias_ld;
   p.bias_flags = a->bias_flags; p.flags_bstride = a->flags_bstride; p.flags_ld = a->flags_ld;
   p.tile_off = a->bias_tile_off;
-  auto kern = fmha_fwd_kernel<D, BF16, HAS_BIAS>;
+  auto kern = fmha_fwd_kernel<D, BF16, HAS_BIAS, POLY_PAIRS>;
   constexpr int SMEM = fmha_smem_bytes<D>();
   static bool attr_set = false;
   if (!attr_set) {
@@ -441,10 +470,33 @@ extern "C" int pf_fmha_fwd(const pf_fmha_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool bf = a->dtype == PF_BF16;
   const bool hb = a->bias != nullptr;
+  // PF_FA_POLY = how many of every 8 key pairs evaluate their exponentials on the FMA pipe (0 = all on the MUFU); measured
+  // default below. Only the head-dim-64 bf16 kernels — the ones that matter for the step — carry the variants.
+  static const int poly = [] {
+    const char* e = getenv("PF_FA_POLY");
+    return e ? atoi(e) : PF_FA_POLY_DEFAULT;
+  }();
   if (a->head_dim == 64) {
-    if (bf) return hb ? launch_fmha<64, true, true>(a, st) : launch_fmha<64, true, false>(a, st);
-    return hb ? launch_fmha<64, false, true>(a, st) : launch_fmha<64, false, false>(a, st);
+    if (bf && !hb) {
+      switch (poly) {
+        case 2: return launch_fmha<64, true, false, 2>(a, st);
+        case 3: return launch_fmha<64, true, false, 3>(a, st);
+        case 4: return launch_fmha<64, true, false, 4>(a, st);
+        default: return launch_fmha<64, true, false, 0>(a, st);
+      }
+    }
+    if (bf) return launch_fmha<64, true, true, 0>(a, st);
+    return hb ? launch_fmha<64, false, true, 0>(a, st) : launch_fmha<64, false, false, 0>(a, st);
   }
-  if (bf) return hb ? launch_fmha<32, true, true>(a, st) : launch_fmha<32, true, false>(a, st);
-  return hb ? launch_fmha<32, false, true>(a, st) : launch_fmha<32, false, false>(a, st);
+  if (bf) {
+    if (hb) {
+      switch (poly) {
+        case 2: return launch_fmha<32, true, true, 2>(a, st);
+        case 3: return launch_fmha<32, true, true, 3>(a, st);
+        default: return launch_fmha<32, true, true, 0>(a, st);
+      }
+    }
+    return launch_fmha<32, true, false, 0>(a, st);
+  }
+  return hb ? launch_fmha<32, false, true, 0>(a, st) : launch_fmha<32, false, false, 0>(a, st);
 }
