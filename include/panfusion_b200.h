@@ -328,7 +328,7 @@ int pf_eppa_pe(const double* cams_e2p, int V, int ph, int pw, int eh, int ew, co
  *   peer_flags    DEVICE array [nranks] of pointers to every rank's nranks flag words (zero-initialised, uint32)
  *   my_flags      == peer_flags[rank];  state: 2 zero-initialised uint32 of this rank (epoch, CTA counter)
  * On return (stream order) the own receive buffer holds every rank's slice in rank order. One kernel: push to all peers,
- * publish the epoch, wait for all peers; a peer that never arrives makes the kernel trap after ~2 s instead of hanging. */
+ * publish the epoch, wait for all peers; a peer that never arrives makes the kernel trap after ~15 s instead of hanging. */
 /* Receive buffers of the device-side collectives: cudaMalloc'ed (zero-filled) by pf_comm_alloc, exported as a 64-byte CUDA IPC
  * handle, opened by the peers ON THEIR device (cudaIpcOpenMemHandle with lazy peer access — NVLink on an HGX board). */
 int pf_comm_alloc(long long bytes, void** ptr);

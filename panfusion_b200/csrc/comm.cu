@@ -160,7 +160,7 @@ extern "C" int pf_allgather_views(const void* local, long long slice_bytes, void
   p.state = state;
   p.rank = rank;
   p.nranks = nranks;
-  p.timeout_cycles = 4000000000LL;  // ~2 s at 1.9 GHz: a missing peer aborts the kernel instead of hanging the GPU
+  p.timeout_cycles = 30000000000LL;  // ~15 s at 1.9 GHz: a missing peer aborts the kernel instead of hanging the GPU
   // enough CTAs to drive NVLink (a slice is 0.3 - 2.6 MB), few enough to leave the SMs to the compute stream
   long long ctas = (p.slice_vecs + 4095) / 4096;  // >= 64 KB per CTA
   if (ctas < 1) ctas = 1;
