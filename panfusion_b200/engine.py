@@ -240,7 +240,9 @@ class Branch:
     def set_text(self, prompt: Tensor, key=None) -> None:
         """prompt [N, L, ctx] -> K/V of every cross-attention layer. The text does not change across denoising steps
         (PanFusion.py:134-138 embeds it once), so the result is cached on the identity + version of the caller's
-        tensor (`key`, taken before any slicing/reshaping)."""
+        tensor (`key`, taken before any slicing/reshaping). In-place edits — also through views, which share the base's
+        version counter — invalidate the entry; only writes through `.data` bypass version tracking (PyTorch-wide caveat):
+        call `MultiViewBaseModel.update_text` / `invalidate()` after such a write."""
         key = key if key is not None else (prompt.data_ptr(), prompt._version, tuple(prompt.shape))
         if key == self._text_key:
             return

@@ -158,7 +158,18 @@ class GraphSegments:
         self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             self._begin()
-            body()
+            try:
+                body()
+            except BaseException:
+                # leave capture mode (otherwise the stream stays unusable) and drop the partial segments
+                if self._cur is not None:
+                    try:
+                        self._cur.capture_end()
+                    except Exception:
+                        pass
+                    self._cur = None
+                self.items.clear()
+                raise
             self._end()
         torch.cuda.current_stream().wait_stream(self.stream)
 
