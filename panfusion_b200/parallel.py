@@ -31,6 +31,10 @@ from torch import Tensor
 DEVICE_GATHER = __import__("os").environ.get("PF_DEVICE_GATHER", "1") != "0"
 
 
+class TransportUnavailable(RuntimeError):
+    """The IPC / peer-access set-up of the device-side all-gather failed on at least one rank of the group."""
+
+
 class _Site:
     __slots__ = ("recv", "ctrl_ptr", "peer_data", "peer_flags", "base", "opened")
 
@@ -55,8 +59,12 @@ class DeviceAllGather:
     passed at least one later collective of the SAME slot sequence (see csrc/comm.cu), which the sampler guarantees by
     cycling through >= 2 slots."""
 
-    def __init__(self, group):
+    def __init__(self, group, agree_group=None):
         self.group = group
+        # the success of a site's set-up is agreed over `agree_group` (ViewParallel passes its whole group: all its ranks
+        # create their n-th site at the same point of the step, each inside its own view group, and must switch transport
+        # together or not at all)
+        self.agree_group = agree_group if agree_group is not None else group
         self.S = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.sites: dict = {}
@@ -69,25 +77,50 @@ class DeviceAllGather:
         nbytes = x.numel() * x.element_size()
         data_bytes = (S * nbytes + 255) // 256 * 256
         site = _Site()
-        base = C.c_void_p()
-        _lib.check(lib.pf_comm_alloc(C.c_longlong(data_bytes + 256), C.byref(base)))
-        site.base = base.value
+        # Every rank runs the SAME sequence of host collectives whatever happens locally, then the group agrees (MIN over
+        # a success flag) on whether the mappings exist everywhere; a failure anywhere makes every rank raise
+        # TransportUnavailable, and ViewParallel falls back to NCCL for the rest of the run (all ranks together).
+        err = None
+        site.base, handle = 0, None
+        try:
+            if __import__("os").environ.get("PF_FORCE_IPC_FAIL", "0") != "0":
+                raise RuntimeError("PF_FORCE_IPC_FAIL is set (test hook)")
+            base = C.c_void_p()
+            _lib.check(lib.pf_comm_alloc(C.c_longlong(data_bytes + 256), C.byref(base)))
+            site.base = base.value
+            hbuf = (C.c_ubyte * 64)()
+            _lib.check(lib.pf_ipc_export(C.c_void_p(site.base), hbuf))
+            handle = bytes(hbuf)
+        except Exception as e:  # noqa: BLE001 - reported below, after the group has agreed
+            err = e
         site.ctrl_ptr = site.base + data_bytes
-        handle = (C.c_ubyte * 64)()
-        _lib.check(lib.pf_ipc_export(C.c_void_p(site.base), handle))
         everyone = [None] * S
-        dist.all_gather_object(everyone, bytes(handle), group=self.group)
+        dist.all_gather_object(everyone, handle, group=self.group)
         data_ptrs, flag_ptrs, site.opened = [], [], []
-        for r, h in enumerate(everyone):
-            if r == self.rank:
-                peer = site.base
-            else:
-                out = C.c_void_p()
-                _lib.check(lib.pf_ipc_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(out)))
-                peer = out.value
-                site.opened.append(peer)
-            data_ptrs.append(peer)
-            flag_ptrs.append(peer + data_bytes)
+        if err is None and all(h is not None for h in everyone):
+            try:
+                for r, h in enumerate(everyone):
+                    if r == self.rank:
+                        peer = site.base
+                    else:
+                        out = C.c_void_p()
+                        _lib.check(lib.pf_ipc_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(out)))
+                        peer = out.value
+                        site.opened.append(peer)
+                    data_ptrs.append(peer)
+                    flag_ptrs.append(peer + data_bytes)
+            except Exception as e:  # noqa: BLE001
+                err = e
+        elif err is None:
+            err = RuntimeError("a peer could not export its receive buffer")
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=x.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.agree_group)
+        if int(ok.item()) == 0:
+            for ptr in site.opened:
+                lib.pf_ipc_close(C.c_void_p(ptr))
+            if site.base:
+                lib.pf_comm_free(C.c_void_p(site.base))
+            raise TransportUnavailable(f"device all-gather set-up failed on a rank of the group ({err})")
         site.peer_data = torch.tensor(data_ptrs, dtype=torch.int64, device=x.device)
         site.peer_flags = torch.tensor(flag_ptrs, dtype=torch.int64, device=x.device)
         if x.dtype not in _TYPESTR:
@@ -200,6 +233,13 @@ class ViewParallel:
         self._dev_world: Optional[DeviceAllGather] = None
         self._slot, self._site = 0, 0
 
+    def _fall_back(self, why: Exception) -> None:
+        """Every rank of the group raised together (DeviceAllGather._create agrees collectively): use NCCL from now on."""
+        import warnings
+        warnings.warn(f"panfusion_b200: {why}; the sharded step uses NCCL all-gathers between CUDA-graph segments instead",
+                      stacklevel=3)
+        self.device_gather = False
+
     def begin_step(self, slot: int = 0) -> None:
         """Called at the start of every forward: `slot` selects the set of receive buffers (see DeviceAllGather)."""
         self._slot, self._site = int(slot), 0
@@ -242,8 +282,12 @@ class ViewParallel:
         bl, L, C = x.shape
         if self.device_gather and x.is_cuda:  # CPU tensors (the gloo plumbing tests) take the torch.distributed path
             if self._dev_view is None:
-                self._dev_view = DeviceAllGather(self.view_group)
-            out = self._dev_view.all_gather(self._next_key(), x.contiguous())
+                self._dev_view = DeviceAllGather(self.view_group, agree_group=self.group)
+            try:
+                out = self._dev_view.all_gather(self._next_key(), x.contiguous())
+            except TransportUnavailable as e:
+                self._fall_back(e)
+                return self.gather_views(x)
         else:
             out = torch.empty((self.view_shards * bl, L, C), dtype=x.dtype, device=x.device)  # concat along dim 0
             xc, grp = x.contiguous(), self.view_group
@@ -261,10 +305,14 @@ class ViewParallel:
         if self.device_gather and pc.is_cuda:
             if self._dev_world is None:
                 self._dev_world = DeviceAllGather(self.group)
-            pano_all = self._dev_world.all_gather(self._next_key(), pc)
-            if sample_loc is not None:
-                sc = sample_loc.contiguous()
-                s_all = self._dev_world.all_gather(self._next_key(), sc)
+            try:
+                pano_all = self._dev_world.all_gather(self._next_key(), pc)
+                if sample_loc is not None:
+                    sc = sample_loc.contiguous()
+                    s_all = self._dev_world.all_gather(self._next_key(), sc)
+            except TransportUnavailable as e:
+                self._fall_back(e)
+                return self.gather_outputs(sample_loc, pano_loc, b, m)
         else:
             pano_all = torch.empty((self.world * pano_loc.shape[0], *pano_loc.shape[1:]), dtype=pano_loc.dtype,
                                    device=pano_loc.device)

@@ -80,6 +80,9 @@ def main():
         if rank == 0:
             print(f"[mgpu] world={world} graph={graph}: |sharded - single| latents {d_lat:.3e} pano {d_pano:.3e} "
                   f"(scale {scale:.2f}) {'OK' if good else 'MISMATCH'}", flush=True)
+    if rank == 0 and os.environ.get("PF_FORCE_IPC_FAIL", "0") != "0":
+        assert model._par.device_gather is False, "the forced IPC failure must have switched the transport to NCCL"
+        print("[mgpu] transport fell back to NCCL as requested by PF_FORCE_IPC_FAIL", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -36,3 +36,18 @@ def test_sharded_matches_single(world, split_k):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env={**os.environ, "PF_SPLIT_K": split_k})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MISMATCH" not in r.stdout
+
+
+def test_transport_falls_back_to_nccl_together():
+    """If the IPC / peer-access set-up of the device all-gather fails on ANY rank (forced here), every rank switches to NCCL at
+    the same collective and the sharded result is unchanged."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    world = min(4, torch.cuda.device_count() // 2 * 2)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29650", str(ROOT / "scripts" / "mgpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
+                       env={**os.environ, "PF_SPLIT_K": "0", "PF_FORCE_IPC_FAIL": "1", "MGPU_GRAPH_MODES": "1"})
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MISMATCH" not in r.stdout and "fell back to NCCL" in r.stdout
