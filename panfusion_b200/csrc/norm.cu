@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256) conv_prep_kernel(const PrepParams p) {
 // produces its share of the image's output positions — the source pixels are re-read from L2, not HBM.
 // sync[3n .. 3n+2] = {arrivals, flag, departures}: all zero on entry and restored to zero by the last CTA to leave.
 // ------------------------------------------------------------------------------------------------
-constexpr int GNP_MAX_SLABS = 32;  // statistics partition of one image (fixed by its size)
+constexpr int GNP_MAX_SLABS = 64;  // upper bound of the statistics partition of one image (fixed by its size)
 constexpr int GNP_MAX_CTAS = 148;  // one CTA per SM; two such launches (2 CTAs of <= 512 threads per SM) stay co-resident
 
 __device__ __forceinline__ int ld_acquire_s32(const int* p) {
@@ -682,8 +682,18 @@ extern "C" int pf_gn_prep(const void* x1, int ld1, int C1, const void* x2, int l
   p.count = float(H) * float(W + 2 * circ_stats) * float(C / groups);
   p.eps = eps;
   const int hw = H * W;
+  static const int max_slabs = [] {
+    const char* e = getenv("PF_GN_SLABS");
+    const int v = e ? atoi(e) : 32;
+    return v < 1 ? 1 : (v > GNP_MAX_SLABS ? GNP_MAX_SLABS : v);
+  }();
+  static const int max_apply_ctas = [] {
+    const char* e = getenv("PF_GN_APPLY_CTAS");
+    const int v = e ? atoi(e) : 64;
+    return v < 1 ? 1 : v;
+  }();
   int slabs = hw / 16;  // >= 16 source pixels per slab; a function of the image size ONLY (batch-invariant sums)
-  slabs = slabs < 1 ? 1 : (slabs > GNP_MAX_SLABS ? GNP_MAX_SLABS : slabs);
+  slabs = slabs < 1 ? 1 : (slabs > max_slabs ? max_slabs : slabs);
   p.slabs = slabs;
   const int vecs = C / 8;
   int ppi = 512 / vecs;
@@ -716,8 +726,8 @@ extern "C" int pf_gn_prep(const void* x1, int ld1, int C1, const void* x2, int l
     else launch_pdl(gn_prep_kernel<false, 1>, g1, dim3(threads), smem, st, p);
     PF_CHECK_LAUNCH("gn_prep_kernel(stats)");
     const int total = phases * p.Ho * p.Wo;
-    int c2 = total / 32;  // >= 32 output positions per CTA
-    c2 = c2 < 1 ? 1 : (c2 > 64 ? 64 : c2);
+    int c2 = total / 16;  // >= 16 output positions per CTA
+    c2 = c2 < 1 ? 1 : (c2 > max_apply_ctas ? max_apply_ctas : c2);
     dim3 g2(c2, N);
     if (dtype == PF_BF16) launch_pdl(gn_prep_kernel<true, 2>, g2, dim3(threads), smem, st, p);
     else launch_pdl(gn_prep_kernel<false, 2>, g2, dim3(threads), smem, st, p);
