@@ -538,6 +538,10 @@ def run_reference(args):
         return
     wl = WORKLOADS[args.workload]
     cores = host_threads()
+    if wl.get("layout_cond"):
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU arm times the un-conditioned loop (workload c2); the "
+                          "layout-conditioned workload adds a ControlNet pass (+7.5 % FLOPs) that is not wired into the timing loop"}))
+        return
     loop = _OracleLoop(args.workload)
     t_warm = loop.step()
     n_timed = max(2, min(args.steps, int(args.ref_budget / max(t_warm, 1e-3))))
