@@ -58,6 +58,8 @@ FUSE_LN = __import__("os").environ.get("PF_FUSE_LN", "1") != "0"
 # GroupNorm statistics + apply + layout as ONE launch (ops.gn_prep) instead of pf_groupnorm_stats -> pf_conv_prep, and the
 # skip concatenation folded into it; same A/B switch idea
 FUSE_GN = __import__("os").environ.get("PF_FUSE_GN", "1") != "0"
+# Transformer2DModel tail: ff2 + residual + proj_out as one GEMM over [f | h] (see _Transformer.tail)
+FUSE_TAIL = __import__("os").environ.get("PF_FUSE_TAIL", "1") != "0"
 
 
 class _LinLN:
@@ -133,6 +135,12 @@ class _Transformer:
         wp, bp = pack_geglu(ff1.weight.detach(), ff1.bias.detach(), self.ff1_bn)
         self.ff1_w, self.ff1_b = wp.to(dev, dt).contiguous(), bp.to(dev)
         self.ff2 = _Lin(ff2.weight, ff2.bias, dev, dt)
+        # ff2 and proj_out back to back are ONE linear map of [f | h]: proj_out(ff2(f) + h) = f (Wp W2)^T + h Wp^T + (Wp b2 + bp).
+        # The GEGLU output f and the residual stream h are written side by side ([T, 4C | C]), so the tail of the block is a
+        # single GEMM with K = 5C (same MACs, one launch and one [T, C] round trip through HBM less).
+        wp, w2 = t.proj_out.weight.detach().double().flatten(1), ff2.weight.detach().double()
+        self.tail = _Lin(torch.cat([wp @ w2, wp], 1).float(),
+                         (wp @ ff2.bias.detach().double() + t.proj_out.bias.detach().double()).float(), dev, dt)
         self.C = self.proj_in.n
         # the three LayerNorms folded into their consumer GEMMs
         self.qkv_ln = _LinLN(torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0), None, blk.norm1, dev, dt)
@@ -345,6 +353,15 @@ class Branch:
                               ln=(st, t.q2_ln.colsum, t.q2_ln.eps)).reshape(N, L, C)
             ops.fmha(q, kv[..., t.kv_off:t.kv_off + C], kv[..., t.kv_off + C:t.kv_off + 2 * C], o, heads=t.heads,
                      head_dim=d, scale=d ** -0.5)
+            if FUSE_TAIL and x.C == C:
+                Fk = t.ff2.k                                   # 4C
+                fh = new(Fk + C)                               # [T, f | h]: A operand of the merged ff2 + proj_out GEMM
+                h, st = ops.gemm_taps(o.reshape(T, C), t.out2.w, fh[:, Fk:], M=T, Kc=C, bias=t.out2.b, residual=h,
+                                      row_stats=True)
+                ops.gemm_taps(h, t.ff1_ln.w, fh[:, :Fk], M=T, Kc=C, bias=t.ff1_ln.b, act=ops.PF_ACT_GEGLU,
+                              block_n=t.ff1_bn, ln=(st, t.ff1_ln.colsum, t.ff1_ln.eps))
+                out = ops.gemm_taps(fh, t.tail.w, new(x.C), M=T, Kc=Fk + C, bias=t.tail.b, residual=x.t)
+                return Img(out, N, H, W)
             h, st = ops.gemm_taps(o.reshape(T, C), t.out2.w, new(C), M=T, Kc=C, bias=t.out2.b, residual=h, row_stats=True)
             f = ops.gemm_taps(h, t.ff1_ln.w, new(t.ff2.k), M=T, Kc=C, bias=t.ff1_ln.b, act=ops.PF_ACT_GEGLU,
                               block_n=t.ff1_bn, ln=(st, t.ff1_ln.colsum, t.ff1_ln.eps))
