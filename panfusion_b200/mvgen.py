@@ -147,7 +147,7 @@ class MultiViewBaseModel(nn.Module):
         if two and self._side is None:
             # the panorama branch (many small launches that every fusion waits for) runs at higher stream priority: 25.9 -> 25.7 ms
             # single GPU, 9.60 -> 9.55 ms for a rank of the 8-GPU layout (PF_SIDE_PRIORITY=0 restores equal priorities)
-            self._side = torch.cuda.Stream(device=dev, priority=int(__import__("os").environ.get("PF_SIDE_PRIORITY", "0")))
+            self._side = torch.cuda.Stream(device=dev, priority=int(__import__("os").environ.get("PF_SIDE_PRIORITY", "-1")))
         side = self._side if two else main
         keep = []  # tensors produced on `main` but consumed on `side`: kept alive until the next join
 
