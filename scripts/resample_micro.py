@@ -37,6 +37,23 @@ for _ in range(10):
 b.record()
 torch.cuda.synchronize()
 print(f"{which}: {a.elapsed_time(b) / 10 * 1e3:.1f} us per call (Python launch path included)")
+# the same call captured in a CUDA graph (20 launches per replay): kernel time without the host launch path
+side = torch.cuda.Stream()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.stream(side):
+    fn()
+    side.synchronize()
+    with torch.cuda.graph(g, stream=side):
+        for _ in range(20):
+            fn()
+g.replay()
+torch.cuda.synchronize()
+a.record()
+for _ in range(5):
+    g.replay()
+b.record()
+torch.cuda.synchronize()
+print(f"{which}: {a.elapsed_time(b) / 100 * 1e3:.1f} us per launch (graph-timed)")
 torch.cuda.profiler.start()
 fn()
 torch.cuda.synchronize()
