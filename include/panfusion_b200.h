@@ -182,7 +182,7 @@ typedef struct pf_fmha_args {
   const uint8_t* bias_flags;
   int64_t flags_bstride;
   int32_t flags_ld;
-  /* tile-PACKED bias (the resident form of the EPPA tables): `bias` is then the store [n_live][128][64] fp32 built by
+  /* tile-PACKED bias (the resident form of the EPPA tables): `bias` is then the store [n_live][128 * 64] fp32 (lane-interleaved tiles) built by
    * pf_bias_tile_pack and bias_tile_off[bias batch][ceil(Lq/128)][ceil(Lk/64)] (row stride flags_ld, batch stride
    * flags_bstride, in tiles) holds each tile's index in it, or -1 for a tile that is entirely -1 (no correspondence).
    * bias_ld / bias_bstride / bias_flags are unused. The reference materialises the dense tensor PER HEAD
@@ -196,7 +196,9 @@ int pf_bias_tile_flags(const float* bias, int G, int Lq, int Lk, int bias_ld, in
                        void* stream);
 /* exclusive scan of the live (flag == 0) tiles: tile_off[t] = index among the live tiles or -1; n_live[0] = their number */
 int pf_bias_tile_scan(const uint8_t* flags, int num_tiles, int32_t* tile_off, int32_t* n_live, void* stream);
-/* packed[tile_off[g][qt][kt]][128][64] <- the dense 128 x 64 tile (zero outside [Lq, Lk]); constant tiles are skipped */
+/* packed[tile_off[g][qt][kt]] <- the dense 128 x 64 tile (zero outside [Lq, Lk]); constant tiles are skipped. Inside a
+ * tile the 8192 floats are LANE-INTERLEAVED for the attention kernel (thread = query row): element (r, c) sits at
+ * (((r / 32) * 16 + c / 4) * 32 + r % 32) * 4 + c % 4, so one 16-byte load of a warp covers 512 contiguous bytes. */
 int pf_bias_tile_pack(const float* bias, int G, int Lq, int Lk, int bias_ld, int64_t bias_bstride, const int32_t* tile_off,
                       float* packed, void* stream);
 

@@ -7,6 +7,8 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 import torch
 
 PF_F32, PF_F16, PF_BF16 = 0, 1, 2
@@ -17,6 +19,8 @@ PF_CAM_DOUBLES = 20
 _DTYPES = {torch.float32: PF_F32, torch.float16: PF_F16, torch.bfloat16: PF_BF16}
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpanfusion_b200.so"
+if os.environ.get("PF_LIB_PATH"):  # A/B of two builds of the SAME C-ABI (scripts/): never a different implementation
+    LIB_PATH = Path(os.environ["PF_LIB_PATH"])
 
 
 class PFError(RuntimeError):

@@ -286,8 +286,12 @@ bias_tile_pack_kernel(const float* __restrict__ bias, int Lq, int Lk, int ld, lo
   const float* base = bias + (long long)g * bstride;
   float* dst = packed + (size_t)off * (128 * 64);
   for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) {
-    const int r = qt * 128 + i / 64, c = kt * 64 + i % 64;
-    dst[i] = (r < Lq && c < Lk) ? __ldg(base + (long long)r * ld + c) : 0.f;
+    const int rl = i / 64, cl = i % 64;
+    const int r = qt * 128 + rl, c = kt * 64 + cl;
+    // lane-interleaved: the attention kernel's thread = query row (warp rl / 32, lane rl % 32) reads 16-byte piece cl / 4;
+    // piece e of one warp is 32 lanes x 16 B = 512 contiguous bytes
+    const int o = (((rl >> 5) * 16 + (cl >> 2)) * 32 + (rl & 31)) * 4 + (cl & 3);
+    dst[o] = (r < Lq && c < Lk) ? __ldg(base + (long long)r * ld + c) : 0.f;
   }
 }
 

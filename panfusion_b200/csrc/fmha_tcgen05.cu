@@ -246,15 +246,20 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int qq = q < p.Lq ? q : p.Lq - 1;
       if (p.tile_off) {
         off_row = p.tile_off + (long long)b * p.flags_bstride + (long long)qt * p.flags_ld;
-        bias_row = p.bias + row * FA_BLOCK_N;  // + tile index * 128 * 64 per key tile
+        bias_row = p.bias + (quarter * (FA_BLOCK_N / 4) * 32 + lane) * 4;  // lane-interleaved tile; + tile index * 128 * 64
       } else {
         bias_row = p.bias + (long long)b * p.bias_bstride + (long long)qq * p.bias_ld;
         if (p.bias_flags) flag_row = p.bias_flags + (long long)b * p.flags_bstride + (long long)qt * p.flags_ld;
       }
     }
-    const float sc = HAS_BIAS ? 1.0f : p.scale_log2;
 
     for (int j = 0; j < n_tiles; ++j) {
+      const int k0 = j * FA_BLOCK_N;
+      // this tile's entry of the packed-bias index (fetching it one iteration ahead measured slower: one more live register)
+      int toff = 0;
+      if constexpr (HAS_BIAS) {
+        if (off_row) toff = off_row[j];
+      }
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       float sv[FA_BLOCK_N];
@@ -271,33 +276,37 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       tc_fence_before();
       mbar_arrive(s_free);
-      const int k0 = j * FA_BLOCK_N;
-      // sv <- logits in log2 units. Without bias the softmax scale is folded into the exp2 argument below (one FFMA
-      // per element); with bias: t = s*scale*log2e + bias*log2e.
+      // Logits in log2 units are sv * sc + shift. Without bias, and on a tile whose bias is the constant -1, the raw scores
+      // stay in sv and (sc, shift) = (scale*log2e, 0 or -log2e) are folded into the exp2 argument below (one FFMA per
+      // element); a live bias tile is added here, t = s*scale*log2e + bias*log2e, and continues with (1, 0).
+      float sc = p.scale_log2, shift = 0.f;
       if constexpr (HAS_BIAS) {
-        const int toff = off_row ? off_row[j] : 0;
         const bool constant_tile = off_row ? toff < 0 : (flag_row != nullptr && flag_row[j] != 0);
         if (constant_tile) {
-#pragma unroll
-          for (int e = 0; e < FA_BLOCK_N; ++e) sv[e] = fmaf(sv[e], p.scale_log2, -LOG2E);
+          shift = -LOG2E;
         } else if (off_row || k0 + FA_BLOCK_N <= p.Lk) {
-          // packed tiles are always full 64-wide rows (zero beyond Lk: those keys are masked below)
+          // A packed tile is lane-interleaved (pf_bias_tile_pack): 16-byte piece e of this warp's 32 rows is 512 contiguous
+          // bytes, one fully coalesced request (a row-major tile costs 32 sectors per request: measured 269 -> 205 us at
+          // the C2 level-32 direction-1 shape). Packed tiles are always full 64-wide (zero beyond Lk: masked below).
           const float4* b4 = off_row ? reinterpret_cast<const float4*>(bias_row + (long long)toff * (FA_BLOCK_M * FA_BLOCK_N))
                                      : reinterpret_cast<const float4*>(bias_row + k0);
+          const int st4 = off_row ? 32 : 1;
 #pragma unroll
           for (int e = 0; e < FA_BLOCK_N / 4; ++e) {
-            const float4 t = __ldg(b4 + e);
+            const float4 t = __ldg(b4 + e * st4);
             sv[4 * e + 0] = fmaf(t.x, LOG2E, sv[4 * e + 0] * p.scale_log2);
             sv[4 * e + 1] = fmaf(t.y, LOG2E, sv[4 * e + 1] * p.scale_log2);
             sv[4 * e + 2] = fmaf(t.z, LOG2E, sv[4 * e + 2] * p.scale_log2);
             sv[4 * e + 3] = fmaf(t.w, LOG2E, sv[4 * e + 3] * p.scale_log2);
           }
-        } else {
+          sc = 1.0f;
+        } else {  // ragged last key tile of a dense table
 #pragma unroll
           for (int e = 0; e < FA_BLOCK_N; ++e) {
             const float bv = (k0 + e < p.Lk) ? __ldg(bias_row + k0 + e) : 0.f;
             sv[e] = fmaf(bv, LOG2E, sv[e] * p.scale_log2);
           }
+          sc = 1.0f;
         }
       }
       if (k0 + FA_BLOCK_N > p.Lk) {
@@ -311,8 +320,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int i = 0; i < 8; ++i) mxs[i] = sv[i];
 #pragma unroll
       for (int e = 8; e < FA_BLOCK_N; ++e) mxs[e & 7] = fmaxf(mxs[e & 7], sv[e]);
-      const float mx_tile = sc * fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
-                                       fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      const float mx_raw = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                                 fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      const float mx_tile = HAS_BIAS ? fmaf(mx_raw, sc, shift) : sc * mx_raw;
       // lazy rescale: raise the reference only when this row would otherwise exceed 2^8
       const bool need = mx_tile > m_used + RESCALE_THRESHOLD;
       bool o_waited = false;
@@ -342,7 +352,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       f32x2 ps2[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) ps2[i] = pack_f2(0.f, 0.f);
-      const f32x2 sc2 = pack_f2(sc, sc), nm2 = pack_f2(-m_used, -m_used);
+      const f32x2 sc2 = pack_f2(sc, sc), nm2 = HAS_BIAS ? pack_f2(shift - m_used, shift - m_used) : pack_f2(-m_used, -m_used);
       uint32_t pk[FA_BLOCK_N / 2];
 #pragma unroll
       for (int e = 0; e < FA_BLOCK_N; e += 2) {

@@ -139,8 +139,9 @@ def bias_tile_flags(bias: Tensor) -> Tensor:
 
 
 def bias_pack_tiles(bias: Tensor):
-    """Dense fp32 bias [G, Lq, Lk] -> (store [n_live, 128, 64] fp32, tile_off int32 [G, ceil(Lq/128), ceil(Lk/64)]): only the
-    128 x 64 tiles that are not entirely -1 are kept (pf_bias_tile_flags -> pf_bias_tile_scan -> pf_bias_tile_pack)."""
+    """Dense fp32 bias [G, Lq, Lk] -> (store [n_live, 128 * 64] fp32, tile_off int32 [G, ceil(Lq/128), ceil(Lk/64)]): only the
+    128 x 64 tiles that are not entirely -1 are kept (pf_bias_tile_flags -> pf_bias_tile_scan -> pf_bias_tile_pack). A stored
+    tile is lane-interleaved for the attention kernel; `bias_tile_dense` gives back its [128, 64] view."""
     assert bias.dtype == torch.float32 and bias.dim() == 3 and bias.stride(2) == 1
     G, Lq, Lk = bias.shape
     flags = bias_tile_flags(bias)
@@ -150,11 +151,16 @@ def bias_pack_tiles(bias: Tensor):
     _count(1)
     _lib.check(lib.pf_bias_tile_scan(_vp(flags), flags.numel(), _vp(tile_off), _vp(n_live), _st()))
     n = int(n_live.item())  # host sync: table construction is a one-off per camera set
-    store = torch.empty((max(n, 1), 128, 64), dtype=torch.float32, device=bias.device)
+    store = torch.empty((max(n, 1), 128 * 64), dtype=torch.float32, device=bias.device)
     _count(1)
     _lib.check(lib.pf_bias_tile_pack(_vp(bias), G, Lq, Lk, bias.stride(1), C.c_int64(bias.stride(0)), _vp(tile_off),
                                      _vp(store), _st()))
     return store, tile_off
+
+
+def bias_tile_dense(tile: Tensor) -> Tensor:
+    """One stored tile [8192] (pf_bias_tile_pack's layout [row / 32][col / 4][row % 32][col % 4]) -> dense [128, 64]."""
+    return tile.reshape(4, 16, 32, 4).permute(0, 2, 1, 3).reshape(128, 64)
 
 
 def fmha(q: Tensor, k: Tensor, v: Tensor, out: Tensor, *, heads: int, head_dim: int, scale: float,
