@@ -110,3 +110,21 @@ def test_row_stats_slots_ignore_tile_requests():
             a.row_stats_out = 1
             seen.add(lib.pf_gemm_row_stats_slots(C.byref(a)))
         assert seen == {want}, (n, seen)
+
+
+def test_packed_bias_tile_layout_helper():
+    """ops.bias_tile_dense inverts the lane-interleaved tile layout documented at pf_bias_tile_pack
+    (include/panfusion_b200.h): element (r, c) of a 128 x 64 tile sits at (((r/32)*16 + c/4)*32 + r%32)*4 + c%4."""
+    import torch
+    from panfusion_b200 import ops
+    dense = torch.arange(128 * 64, dtype=torch.float32).reshape(128, 64)
+    r, c = torch.meshgrid(torch.arange(128), torch.arange(64), indexing="ij")
+    pos = (((r // 32) * 16 + c // 4) * 32 + r % 32) * 4 + c % 4
+    assert sorted(pos.flatten().tolist()) == list(range(128 * 64))  # a permutation of the tile
+    stored = torch.empty(128 * 64)
+    stored[pos.flatten()] = dense.flatten()
+    assert torch.equal(ops.bias_tile_dense(stored), dense)
+    # one 16-byte piece of a warp = 32 lanes x 4 floats, contiguous
+    w, e = 2, 5
+    piece = stored[((w * 16 + e) * 32) * 4:((w * 16 + e) * 32 + 32) * 4].reshape(32, 4)
+    assert torch.equal(piece, dense[w * 32:(w + 1) * 32, e * 4:(e + 1) * 4])
