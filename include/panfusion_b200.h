@@ -293,6 +293,21 @@ int pf_timestep_embed(const float* t, void* out, int dtype, int n, int dim, void
 int pf_embed_tokens(const long long* ids, const float* tok_emb, const float* pos_emb, void* out, int dtype,
                     float* row_stats, int T, int L, int C, int vocab, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Forward half of the training step (models/pano/PanFusion.py:64-98). The backward of the UNets, of
+ * EPPA and of the LoRA adapters, the optimizer and the gradient all-reduce are NOT built.
+ * pf_add_noise: diffusers SchedulerMixin.add_noise [3P] as called at PanFusion.py:84-85 —
+ *   out[b, :] = sqrt(abar[t[b]]) * x0[b, :] + sqrt(1 - abar[t[b]]) * noise[b, :]   (fp32 [B, per_sample], t int64 [B],
+ *   abar = alphas_cumprod fp32 [num_train_timesteps]; a timestep outside the table traps).
+ * pf_mse_loss: torch.nn.functional.mse_loss(a, b) with mean reduction (PanFusion.py:92-93), out[0] = sum((a-b)^2) / n,
+ *   summed in a launch-independent order (fixed chunks, partials added in index order in fp64). ws: pf_mse_loss_ws_floats()
+ *   floats; counter: one zero-initialised int32, re-armed by the kernel.
+ * ------------------------------------------------------------------------------------------------ */
+int pf_add_noise(const float* x0, const float* noise, float* out, const long long* t, const float* alphas_cumprod,
+                 int num_train_timesteps, int B, long long per_sample, void* stream);
+int pf_mse_loss_ws_floats(void);
+int pf_mse_loss(const float* a, const float* b, long long n, float* ws, int* counter, float* out, void* stream);
+
 /* Classifier-free-guidance combine + DDIM update (+ roll of the result by `roll` columns):
  *   e = eps[0:count] + guidance * (eps[count:2count] - eps[0:count])        (PanoGenerator.py:253-262)
  *   out[.., (col+roll) % W] = sqrt(a_prev) * (x - sqrt(1-a_t) e) / sqrt(a_t) + sqrt(1-a_prev) e   (DDIM, eta 0)

@@ -293,6 +293,62 @@ cfg_ddim_kernel(const float* __restrict__ x, const float* __restrict__ eps, floa
   out[o] = v;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Forward half of the training step (models/pano/PanFusion.py:64-98; SURVEY.md 8f rank 4 — the backward is not built)
+// ------------------------------------------------------------------------------------------------
+// diffusers SchedulerMixin.add_noise [3P] as called at PanFusion.py:84-85: one timestep per sample,
+// out = sqrt(abar[t]) * x0 + sqrt(1 - abar[t]) * noise, every product and the sum rounded separately like the eager ops.
+__global__ void __launch_bounds__(256)
+add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise, float* __restrict__ out,
+                 const long long* __restrict__ t, const float* __restrict__ abar, int T, long long per_sample) {
+  const int b = blockIdx.y;
+  const long long tt = t[b];
+  if (tt < 0 || tt >= T) __trap();  // torch raises IndexError
+  const float a = __ldg(abar + tt);
+  const float sa = __fsqrt_rn(a), s1 = __fsqrt_rn(__fsub_rn(1.0f, a));
+  const long long base = (long long)b * per_sample;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x)
+    out[base + i] = __fadd_rn(__fmul_rn(sa, __ldg(x0 + base + i)), __fmul_rn(s1, __ldg(noise + base + i)));
+}
+
+constexpr int MSE_CTAS = 296;  // fixed partition (2 per SM): the summation order never depends on the launch
+
+// torch.nn.functional.mse_loss, mean reduction (PanFusion.py:92-93). Deterministic: element i always belongs to CTA
+// i / chunk, a CTA sums its chunk in a fixed thread-strided order, the last CTA to finish adds the MSE_CTAS partials in
+// index order in fp64 and re-arms the counter.
+__global__ void __launch_bounds__(256)
+mse_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float* __restrict__ ws,
+                int* __restrict__ counter, float* __restrict__ out) {
+  __shared__ float red[8];
+  __shared__ int s_last;
+  const long long chunk = (n + MSE_CTAS - 1) / MSE_CTAS;
+  const long long lo = (long long)blockIdx.x * chunk, hi = (lo + chunk < n) ? lo + chunk : n;
+  float acc = 0.f;
+  for (long long i = lo + threadIdx.x; i < hi; i += 256) {
+    const float d = __ldg(a + i) - __ldg(b + i);
+    acc = fmaf(d, d, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w];
+    ws[blockIdx.x] = s;
+    __threadfence();
+    s_last = (atomicAdd(counter, 1) == MSE_CTAS - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double tot = 0.0;
+    for (int i = 0; i < MSE_CTAS; ++i) tot += (double)__ldcg(ws + i);
+    out[0] = (float)(tot / (double)n);
+    *counter = 0;
+  }
+}
+
 }  // namespace pf
 
 extern "C" int pf_conv_in(const float* x, const float* w, const float* bias, void* out, int dtype, int N, int Cin,
@@ -490,5 +546,28 @@ extern "C" int pf_cfg_ddim_step_dev(const float* x, const float* eps, float* out
   cfg_ddim_kernel<<<(unsigned)((count + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, eps, out, count, W, roll, guidance, 0.f, 0.f, coef);
   PF_CHECK_LAUNCH("cfg_ddim_kernel");
+  return PF_OK;
+}
+
+extern "C" int pf_add_noise(const float* x0, const float* noise, float* out, const long long* t, const float* alphas_cumprod,
+                            int num_train_timesteps, int B, long long per_sample, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(x0 && noise && out && t && alphas_cumprod && num_train_timesteps > 0 && B > 0 && B <= 65535 && per_sample > 0,
+               "pf_add_noise: bad arguments");
+  long long bx = (per_sample + 255) / 256;
+  if (bx > 1184) bx = 1184;
+  add_noise_kernel<<<dim3((unsigned)bx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(x0, noise, out, t, alphas_cumprod,
+                                                                                        num_train_timesteps, per_sample);
+  PF_CHECK_LAUNCH("add_noise_kernel");
+  return PF_OK;
+}
+
+extern "C" int pf_mse_loss_ws_floats(void) { return pf::MSE_CTAS; }
+
+extern "C" int pf_mse_loss(const float* a, const float* b, long long n, float* ws, int* counter, float* out, void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(a && b && ws && counter && out && n > 0, "pf_mse_loss: bad arguments");
+  mse_loss_kernel<<<MSE_CTAS, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n, ws, counter, out);
+  PF_CHECK_LAUNCH("mse_loss_kernel");
   return PF_OK;
 }

@@ -383,6 +383,37 @@ def cfg_ddim_step_dev(x: Tensor, eps: Tensor, out: Tensor, guidance: float, coef
     return out
 
 
+def add_noise(x0: Tensor, noise: Tensor, t: Tensor, alphas_cumprod: Tensor) -> Tensor:
+    """diffusers add_noise (PanFusion.py:84-85): x0, noise fp32 [B, ...], t int64 [B], alphas_cumprod fp32 [T] -> fp32 like x0."""
+    _lib.require_cuda(x0, noise, t, alphas_cumprod)
+    assert x0.dtype == noise.dtype == alphas_cumprod.dtype == torch.float32 and t.dtype == torch.int64
+    assert x0.shape == noise.shape and x0.is_contiguous() and noise.is_contiguous() and t.is_contiguous()
+    assert t.numel() == x0.shape[0] and alphas_cumprod.is_contiguous()
+    out = torch.empty_like(x0)
+    _count(1)
+    _lib.check(_lib.lib().pf_add_noise(_vp(x0), _vp(noise), _vp(out), _vp(t), _vp(alphas_cumprod), alphas_cumprod.numel(),
+                                       x0.shape[0], C.c_longlong(x0.numel() // x0.shape[0]), _st()))
+    return out
+
+
+_MSE_WS = {}
+
+
+def mse_loss(a: Tensor, b: Tensor) -> Tensor:
+    """torch.nn.functional.mse_loss(a, b) (mean; PanFusion.py:92-93) -> fp32 scalar tensor, launch-independent summation order."""
+    _lib.require_cuda(a, b)
+    assert a.dtype == b.dtype == torch.float32 and a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    lib = _lib.lib()
+    ent = _MSE_WS.get(a.device)
+    if ent is None:  # per-device partials + counter; calls on one device are ordered by the stream they are issued on
+        ent = _MSE_WS[a.device] = (torch.empty(lib.pf_mse_loss_ws_floats(), dtype=torch.float32, device=a.device),
+                                   torch.zeros(1, dtype=torch.int32, device=a.device))
+    out = torch.empty((), dtype=torch.float32, device=a.device)
+    _count(1)
+    _lib.check(lib.pf_mse_loss(_vp(a), _vp(b), C.c_longlong(a.numel()), _vp(ent[0]), _vp(ent[1]), _vp(out), _st()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # EPPA tables
 # ------------------------------------------------------------------------------------------------

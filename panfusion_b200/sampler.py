@@ -51,6 +51,17 @@ class DDIMSchedule:
         return sa, math.sqrt(1.0 - a_prev) - sa * math.sqrt(1.0 - a_t)
 
 
+def init_noise(bs, equi_h, equi_w, pers_h, pers_w, cameras, device, generator=None):
+    """PanFusion.init_noise (PanFusion.py:30-43): one panorama noise field per sample; every view's noise is its
+    nearest-neighbour e2p resampling. Shared by the sampler and the training-step forward (training.py)."""
+    cams = {k: v.flatten(0, 1) for k, v in cameras.items()}
+    m = len(cams["FoV"]) // bs
+    pano_noise = torch.randn(bs, 1, 4, equi_h, equi_w, device=device, generator=generator)
+    noise = geometry.e2p(pano_noise[:, 0], cams["FoV"], cams["theta"], cams["phi"], (pers_h, pers_w), mode="nearest",
+                         views_per_image=m)  # = e2p of the panorama expanded to its m views (PanFusion.py:33-37)
+    return pano_noise, noise.reshape(bs, m, *noise.shape[1:])
+
+
 class PanFusionSampler:
     def __init__(self, mv_base_model, guidance_scale: float = 9.0, diff_timestep: int = 50, rot_diff: float = 90.0,
                  use_cuda_graph: bool = True):
@@ -67,12 +78,7 @@ class PanFusionSampler:
 
     # ---- PanFusion.py:30-43 -------------------------------------------------------------------------
     def init_noise(self, bs, equi_h, equi_w, pers_h, pers_w, cameras, device, generator=None):
-        cams = {k: v.flatten(0, 1) for k, v in cameras.items()}
-        m = len(cams["FoV"]) // bs
-        pano_noise = torch.randn(bs, 1, 4, equi_h, equi_w, device=device, generator=generator)
-        noise = geometry.e2p(pano_noise[:, 0], cams["FoV"], cams["theta"], cams["phi"], (pers_h, pers_w), mode="nearest",
-                             views_per_image=m)  # = e2p of the panorama expanded to its m views (PanFusion.py:33-37)
-        return pano_noise, noise.reshape(bs, m, *noise.shape[1:])
+        return init_noise(bs, equi_h, equi_w, pers_h, pers_w, cameras, device, generator)
 
     # ---- PanFusion.py:114-123 / PanoGenerator.py:264-269 ------------------------------------------
     def rotate_latent(self, pano_latent, cameras, degree=None):
