@@ -303,6 +303,12 @@ int pf_embed_tokens(const long long* ids, const float* tok_emb, const float* pos
  *   summed in a launch-independent order (fixed chunks, partials added in index order in fp64). ws: pf_mse_loss_ws_floats()
  *   floats; counter: one zero-initialised int32, re-armed by the kernel.
  * ------------------------------------------------------------------------------------------------ */
+/* Latent sampling at the end of the VAE encoder (diffusers DiagonalGaussianDistribution.sample [3P] + the scaling of
+ * PanoGenerator.encode_image, models/pano/PanoGenerator.py:218-224): moments = channels-last rows of width ld holding
+ * [mean (L) | logvar (L) | ...] for N images of HW pixels; eps, out NCHW fp32 [N, L, HW];
+ * out = (mean + exp(0.5 * clamp(logvar, -30, 20)) * eps) * scale. */
+int pf_gaussian_sample(const float* moments, int ld, const float* eps, float* out, int N, int L, int HW, float scale,
+                       void* stream);
 int pf_add_noise(const float* x0, const float* noise, float* out, const long long* t, const float* alphas_cumprod,
                  int num_train_timesteps, int B, long long per_sample, void* stream);
 int pf_mse_loss_ws_floats(void);

@@ -1,4 +1,5 @@
-"""Oracle: the image-space tail of the sampling loop — VAE decode with circular latent padding + `tensor_to_image`.
+"""Oracle: the image-space ends of the loop — VAE decode with circular latent padding + `tensor_to_image` after sampling,
+and the training step's `encode_image` with circular image padding (PanoGenerator.py:214-225, PanFusion.py:66-71) before it.
 
 First-party code restated: `decode_latent` (models/pano/PanoGenerator.py:272-278),
 `pad_pano(latent=True)` / `unpad_pano` around the panorama decode (PanFusion.py:166-172, PanoGenerator.py:227-238,
@@ -102,6 +103,76 @@ class MidBlock2D(nn.Module):
         return self.resnets[1](x)
 
 
+class Downsample2D(nn.Module):
+    """diffusers Downsample2D(padding=0) as the VAE encoder uses it: zero-pad right and bottom by one, 3x3 stride-2 conv."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.channels = self.out_channels = channels
+        self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=0)
+
+    def forward(self, x):
+        return self.conv(F.pad(x, (0, 1, 0, 1), mode="constant", value=0))
+
+
+class DownEncoderBlock2D(nn.Module):
+    def __init__(self, cin, cout, layers, add_downsample, groups):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, groups) for i in range(layers)])
+        self.downsamplers = nn.ModuleList([Downsample2D(cout)]) if add_downsample else None
+
+    def forward(self, x):
+        for r in self.resnets:
+            x = r(x)
+        if self.downsamplers is not None:
+            for d in self.downsamplers:
+                x = d(x)
+        return x
+
+
+class Encoder(nn.Module):
+    """diffusers Encoder (double_z): conv_in, DownEncoderBlock2D x len(block_out_channels), mid block, GroupNorm / SiLU /
+    conv_out to 2 * latent_channels."""
+
+    def __init__(self, in_channels, latent_channels, block_out_channels, layers_per_block, norm_num_groups):
+        super().__init__()
+        boc, g = tuple(block_out_channels), norm_num_groups
+        self.conv_in = nn.Conv2d(in_channels, boc[0], 3, padding=1)
+        self.down_blocks = nn.ModuleList()
+        out = boc[0]
+        for i, c in enumerate(boc):
+            prev, out = out, c
+            self.down_blocks.append(DownEncoderBlock2D(prev, out, layers_per_block, i != len(boc) - 1, g))
+        self.mid_block = MidBlock2D(boc[-1], g)
+        self.conv_norm_out = nn.GroupNorm(g, boc[-1], eps=1e-6)
+        self.conv_act = nn.SiLU()
+        self.conv_out = nn.Conv2d(boc[-1], 2 * latent_channels, 3, padding=1)
+
+    def forward(self, x):
+        x = self.conv_in(x)
+        for blk in self.down_blocks:
+            x = blk(x)
+        x = self.mid_block(x)
+        return self.conv_out(self.conv_act(self.conv_norm_out(x)))
+
+
+class DiagonalGaussianDistribution:
+    """diffusers DiagonalGaussianDistribution: moments = [mean | logvar] along the channels, logvar clamped to [-30, 20]."""
+
+    def __init__(self, parameters):
+        self.mean, logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+
+    def sample(self, generator=None, noise=None):
+        if noise is None:
+            noise = torch.randn(self.mean.shape, generator=generator, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
+
+    def mode(self):
+        return self.mean
+
+
 class Decoder(nn.Module):
     def __init__(self, latent_channels, out_channels, block_out_channels, layers_per_block, norm_num_groups):
         super().__init__()
@@ -126,7 +197,7 @@ class Decoder(nn.Module):
 
 
 class AutoencoderKL(nn.Module):
-    """Decoder half only (`post_quant_conv`, `decoder`); `decode(z).sample` like diffusers."""
+    """`decode(z).sample` and `encode(x).latent_dist` like diffusers (`post_quant_conv`, `decoder`, `quant_conv`, `encoder`)."""
 
     def __init__(self, latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
                  norm_num_groups=32, scaling_factor=0.18215):
@@ -136,6 +207,9 @@ class AutoencoderKL(nn.Module):
                                       norm_num_groups=norm_num_groups, scaling_factor=scaling_factor)
         self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
         self.decoder = Decoder(latent_channels, out_channels, block_out_channels, layers_per_block, norm_num_groups)
+        # the encoder half is created AFTER the decoder so that the decoder's seeded weights (build_vae) do not move
+        self.quant_conv = nn.Conv2d(2 * latent_channels, 2 * latent_channels, 1)
+        self.encoder = Encoder(out_channels, latent_channels, block_out_channels, layers_per_block, norm_num_groups)
 
     @property
     def dtype(self):
@@ -143,6 +217,9 @@ class AutoencoderKL(nn.Module):
 
     def decode(self, z):
         return SimpleNamespace(sample=self.decoder(self.post_quant_conv(z)))
+
+    def encode(self, x):
+        return SimpleNamespace(latent_dist=DiagonalGaussianDistribution(self.quant_conv(self.encoder(x))))
 
 
 def build_vae(config: dict = SD2_VAE_CONFIG, seed: int = 21) -> AutoencoderKL:
@@ -161,6 +238,20 @@ def decode_latent(latents, vae):
     z = (1 / vae.config.scaling_factor * latents).flatten(0, 1)
     image = vae.decode(z.to(vae.dtype)).sample
     return image.reshape(b, -1, *image.shape[1:])
+
+
+def encode_image(x_input, vae, generator=None, noise=None):
+    """PanoGenerator.py:214-225: [b, l, 3, H, W] in [-1, 1] -> sampled latents [b, l, 4, H/8, W/8] * scaling_factor."""
+    b = x_input.shape[0]
+    dist = vae.encode(x_input.to(vae.dtype).flatten(0, 1)).latent_dist
+    z = dist.sample(generator=generator, noise=noise)
+    z = z.reshape(b, -1, *z.shape[1:])
+    return z * vae.config.scaling_factor
+
+
+def encode_pano(pano, vae, latent_pad: int = 8, generator=None, noise=None):
+    """PanFusion.py:69-71: pad the IMAGE circularly by 8 * latent_pad pixels, encode, crop latent_pad latent columns."""
+    return unpad_pano(encode_image(pad_pano(pano, 8 * latent_pad), vae, generator, noise), latent_pad)
 
 
 def decode_pano(pano_latent, vae, latent_pad: int = 8):

@@ -349,6 +349,25 @@ mse_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, long l
   }
 }
 
+// diffusers DiagonalGaussianDistribution.sample + the scaling of PanoGenerator.encode_image (PanoGenerator.py:218-224):
+// moments are channels-last rows [mean(0..L) | logvar(L..2L) | ...] (the fp32 output tile of the encoder's last tap-GEMM),
+// eps and out are NCHW. z = (mean + exp(0.5 * clamp(logvar, -30, 20)) * eps) * scale, products and sum rounded separately.
+__global__ void __launch_bounds__(256)
+gaussian_sample_kernel(const float* __restrict__ moments, int ld, const float* __restrict__ eps, float* __restrict__ out,
+                       long long total, int L, int HW, float scale) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over out [N, L, HW]
+  if (idx >= total) return;
+  const int px = int(idx % HW);
+  const long long r = idx / HW;
+  const int c = int(r % L);
+  const long long n = r / L;
+  const float* row = moments + (n * HW + px) * (long long)ld;
+  const float mean = __ldg(row + c);
+  const float logvar = fminf(fmaxf(__ldg(row + L + c), -30.0f), 20.0f);
+  const float stdv = expf(__fmul_rn(0.5f, logvar));
+  out[idx] = __fmul_rn(__fadd_rn(mean, __fmul_rn(stdv, __ldg(eps + idx))), scale);
+}
+
 }  // namespace pf
 
 extern "C" int pf_conv_in(const float* x, const float* w, const float* bias, void* out, int dtype, int N, int Cin,
@@ -569,5 +588,16 @@ extern "C" int pf_mse_loss(const float* a, const float* b, long long n, float* w
   PF_CHECK_ARG(a && b && ws && counter && out && n > 0, "pf_mse_loss: bad arguments");
   mse_loss_kernel<<<MSE_CTAS, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n, ws, counter, out);
   PF_CHECK_LAUNCH("mse_loss_kernel");
+  return PF_OK;
+}
+
+extern "C" int pf_gaussian_sample(const float* moments, int ld, const float* eps, float* out, int N, int L, int HW, float scale,
+                                  void* stream) {
+  using namespace pf;
+  PF_CHECK_ARG(moments && eps && out && N > 0 && L > 0 && HW > 0 && ld >= 2 * L, "pf_gaussian_sample: bad arguments");
+  const long long total = (long long)N * L * HW;
+  gaussian_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(moments, ld, eps, out,
+                                                                                                       total, L, HW, scale);
+  PF_CHECK_LAUNCH("gaussian_sample_kernel");
   return PF_OK;
 }

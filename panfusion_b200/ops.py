@@ -396,6 +396,18 @@ def add_noise(x0: Tensor, noise: Tensor, t: Tensor, alphas_cumprod: Tensor) -> T
     return out
 
 
+def gaussian_sample(moments: Tensor, eps: Tensor, latent_channels: int, scale: float) -> Tensor:
+    """moments fp32 [N*HW, ld] rows = [mean | logvar | ...], eps fp32 NCHW [N, L, h, w] -> z fp32 NCHW (pf_gaussian_sample)."""
+    _lib.require_cuda(moments, eps)
+    assert moments.dtype == eps.dtype == torch.float32 and moments.dim() == 2 and moments.stride(1) == 1 and eps.is_contiguous()
+    N, L, h, w = eps.shape
+    assert L == latent_channels and moments.shape[0] == N * h * w and moments.shape[1] >= 2 * L
+    out = torch.empty_like(eps)
+    _count(1)
+    _lib.check(_lib.lib().pf_gaussian_sample(_vp(moments), moments.stride(0), _vp(eps), _vp(out), N, L, h * w, _f(scale), _st()))
+    return out
+
+
 _MSE_WS = {}
 
 

@@ -4,8 +4,9 @@ timestep to the loss — `init_noise` (PanFusion.py:30-43), `scheduler.add_noise
 the CUDA kernels of the denoise path plus `pf_add_noise` / `pf_mse_loss`.
 
 SURVEY.md 8f rank 4 names the whole training step; what is NOT built is everything after the loss: the backward of both
-UNets, of EPPA and of the LoRA adapters, the optimizer and the gradient all-reduce — and the VAE *encoder* before it
-(`encode_image`, PanFusion.py:66-71), so the clean latents are inputs here. `TrainingStep.loss` is therefore a validation /
+UNets, of EPPA and of the LoRA adapters, the optimizer and the gradient all-reduce. The clean latents come from
+`TrainingStep.encode` (`encode_image` on the views and on the circularly padded panorama, PanFusion.py:66-71, on
+`panfusion_b200.vae.VAEEncoder`) or from the caller. `TrainingStep.loss` is therefore a validation /
 monitoring quantity (the number the reference logs as train/loss), not a trainable graph: the returned tensors carry no
 autograd history and `backward()` raises.
 """
@@ -32,6 +33,14 @@ class TrainingStep:
         if a is None:
             a = self._abar[device] = self.scheduler.alphas_cumprod.to(device=device, dtype=torch.float32).contiguous()
         return a
+
+    @staticmethod
+    def encode(images: Tensor, pano: Tensor, vae, latent_pad: int = 8, generator=None):
+        """PanFusion.py:66-71: images [b, m, 3, H, W], pano [b, 1, 3, He, We] in [-1, 1] -> (latents, pano_latent); the
+        panorama is padded circularly in IMAGE space by 8 * latent_pad pixels, encoded, and cropped in latent space.
+        vae: panfusion_b200.vae.VAEEncoder."""
+        from .vae import encode_image, encode_pano
+        return encode_image(images, vae, generator=generator), encode_pano(pano, vae, latent_pad, generator=generator)
 
     def add_noise(self, x0: Tensor, noise: Tensor, t: Tensor) -> Tensor:
         """scheduler.add_noise(x0, noise, t) with one timestep per leading-dim sample (PanFusion.py:84-85)."""

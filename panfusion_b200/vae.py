@@ -1,5 +1,6 @@
 """Image-space tail of the sampling loop: VAE decode with circular latent padding + `tensor_to_image`
- behind the reference's function names.
+ behind the reference's function names — and, for the training step's forward half (§8f rank 4), the
+VAE encoder behind `encode_image` (PanoGenerator.py:214-225) with the circular IMAGE padding of PanFusion.py:69-71.
 
 Reference: `decode_latent` models/pano/PanoGenerator.py:272-278, the padded panorama decode PanFusion.py:166-172
 (`pad_pano(latent=True)` with `latent_pad = 8`, PanoGenerator.py:227-238), `tensor_to_image`
@@ -173,6 +174,136 @@ class VAEDecoder:
         ops.gemm_taps(xp, p.conv_out_packed, o, M=x.N * Hp * Wp, Kc=x.C, taps=taps3x3(Wp), bias=p.conv_out_bpad,
                       image_map=(Hp, Wp, 1, 1, x.H, x.W), block_n=64)
         return o[:, :p.conv_out_c].reshape(x.N, x.H, x.W, p.conv_out_c).permute(0, 3, 1, 2).contiguous()
+
+
+# ---- encoder (training step only: PanoGenerator.encode_image, PanFusion.py:66-71) ---------------------------------------------
+
+class VAEEncoderPack:
+    def __init__(self, vae, dev, dt):
+        self.dev, self.dt = dev, dt
+        e = vae.encoder
+        self.groups = int(e.conv_norm_out.num_groups)
+        self.scaling_factor = float(vae.config.scaling_factor)
+        self.latent_channels = int(vae.quant_conv.weight.shape[0]) // 2
+        self.conv_in_w = e.conv_in.weight.detach().to(dev, torch.float32).contiguous()   # [C0, 3, 3, 3]
+        self.conv_in_b = e.conv_in.bias.detach().to(dev, torch.float32).contiguous()
+        self.down = []
+        for blk in e.down_blocks:
+            self.down.append(dict(resnets=[_VResnet(r, dev, dt) for r in blk.resnets],
+                                  down=[_Conv3(d.conv, dev, dt) for d in blk.downsamplers] if blk.downsamplers is not None else None))
+        self.mid_res = [_VResnet(r, dev, dt) for r in e.mid_block.resnets]
+        a = e.mid_block.attentions[0]
+        self.att_norm = _Norm(a.group_norm, dev)
+        self.att_qk = _Lin(torch.cat([a.to_q.weight, a.to_k.weight], 0), torch.cat([a.to_q.bias, a.to_k.bias], 0), dev, dt)
+        self.att_v = a.to_v.weight.detach().to(dev, dt).contiguous()
+        wo, bo = a.to_out[0].weight.detach().double(), a.to_out[0].bias.detach().double()
+        self.att_out = _Lin(a.to_out[0].weight, (bo + wo @ a.to_v.bias.detach().double()).float(), dev, dt)
+        self.C_mid = self.att_out.n
+        self.norm_out = _Norm(e.conv_norm_out, dev)
+        # quant_conv (1x1, 2L -> 2L) folded EXACTLY into conv_out: W' = Wq W_out, b' = Wq b_out + bq; padded to one 64-wide tile
+        wq = vae.quant_conv.weight.detach().double().flatten(1)            # [2L, 2L]
+        bq = vae.quant_conv.bias.detach().double()
+        wc = e.conv_out.weight.detach().double()                           # [2L, C, 3, 3]
+        w2 = torch.einsum("oc,cits->oits", wq, wc)
+        b2 = wq @ e.conv_out.bias.detach().double() + bq
+        co = w2.shape[0]
+        wpad = torch.zeros((64, *w2.shape[1:]), dtype=torch.float32)
+        wpad[:co] = w2.float()
+        self.conv_out_packed = pack_conv3x3(wpad).to(dev, dt).contiguous()
+        self.conv_out_bpad = torch.zeros(64, dtype=torch.float32, device=dev)
+        self.conv_out_bpad[:co] = b2.float().to(dev)
+
+
+class _EncoderBranch(_DecoderBranch):
+    """The decoder's resnet / attention blocks plus the encoder's Downsample2D: zero-pad right and bottom by one, 3x3
+    stride-2 convolution (diffusers Downsample2D(padding=0) [3P]). Like Branch.downsample it runs on the four stride-2 phases
+    of the zero-haloed image; the taps start one pixel later because there is no padding on the left / top:
+    out(i, j) = sum w[dy, dx] x[2i + dy, 2j + dx]."""
+
+    def downsample(self, x: Img, d: _Conv3) -> Img:
+        N, H, W = x.N, x.H, x.W
+        if H % 2 or W % 2:
+            raise NotImplementedError(f"VAE encoder needs even image sizes at every level (got {H}x{W})")
+        a = ops.conv_prep(x.t, N, H, W, phases=4, halo=1)
+        Ho, Wo = H // 2, W // 2
+        Hq, Wq = Ho + 1, Wo + 1
+        PS = N * Hq * Wq
+        # phase (a, b) holds x[2i + a - 1, 2j + b - 1]: x[2i + dy] = phase (dy + 1) % 2 at row i + (dy + 1) // 2
+        taps = [(((dy + 1) % 2) * 2 + ((dx + 1) % 2)) * PS + ((dy + 1) // 2) * Wq + ((dx + 1) // 2)
+                for dy in range(3) for dx in range(3)]
+        out = torch.empty((N * Ho * Wo, d.cout), dtype=self.dt, device=x.t.device)
+        ops.gemm_taps(a, d.w, out, M=PS, Kc=d.cin, taps=taps, bias=d.b, image_map=(Hq, Wq, 0, 0, Ho, Wo))
+        return Img(out, N, Ho, Wo)
+
+
+class VAEEncoder:
+    """`VAEEncoder(vae).encode(x, noise)` == `vae.encode(x).latent_dist.sample()` for x [N, 3, H, W] in [-1, 1] -> fp32
+    [N, 4, H/8, W/8] (optionally times scaling_factor), on the kernels of the decoder + `pf_gaussian_sample`."""
+
+    def __init__(self, vae, compute_dtype=torch.bfloat16):
+        self.vae, self.compute_dtype = vae, compute_dtype
+        self.config = vae.config
+        self._b: Optional[_EncoderBranch] = None
+
+    def prepare(self, device=None, dtype=None) -> "VAEEncoder":
+        device = torch.device(device or "cuda")
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        _lib.check(_lib.lib().pf_check_device())
+        self._b = _EncoderBranch(VAEEncoderPack(self.vae, device, dtype or self.compute_dtype))
+        return self
+
+    @torch.no_grad()
+    def moments(self, x: Tensor):
+        """-> (fp32 rows [N*h*w, 64] whose first 2L columns are mean | logvar after quant_conv, N, h, w)."""
+        _lib.require_cuda(x)
+        if self._b is None or self._b.p.dev != x.device:
+            self.prepare(x.device)
+        b = self._b
+        p = b.p
+        N, _, H, W = x.shape
+        h = Img(ops.conv_in(x.to(torch.float32).contiguous(), p.conv_in_w, p.conv_in_b, b.dt, False), N, H, W)
+        for blk in p.down:
+            for r in blk["resnets"]:
+                h = b.resnet(h, r)
+            if blk["down"] is not None:
+                for d in blk["down"]:
+                    h = b.downsample(h, d)
+        h = b.resnet(h, p.mid_res[0])
+        h = b.attention(h)
+        h = b.resnet(h, p.mid_res[1])
+        st = ops.groupnorm_stats(h.t, h.N, h.H, h.W, p.groups, p.norm_out.eps, 0)
+        xp = ops.conv_prep(h.t, h.N, h.H, h.W, stats=st, gamma=p.norm_out.g, beta=p.norm_out.b, groups=p.groups,
+                           act=ops.PF_ACT_SILU, halo=1)
+        Hp, Wp = h.H + 2, h.W + 2
+        o = torch.empty((h.N * h.H * h.W, 64), dtype=torch.float32, device=x.device)
+        ops.gemm_taps(xp, p.conv_out_packed, o, M=h.N * Hp * Wp, Kc=h.C, taps=taps3x3(Wp), bias=p.conv_out_bpad,
+                      image_map=(Hp, Wp, 1, 1, h.H, h.W), block_n=64)
+        return o, h.N, h.H, h.W
+
+    @torch.no_grad()
+    def encode(self, x: Tensor, noise: Optional[Tensor] = None, generator=None, scale: bool = False) -> Tensor:
+        """noise: the standard-normal draw of `latent_dist.sample()` ([N, 4, h, w]); drawn on the device when None.
+        scale=True multiplies by vae.config.scaling_factor (encode_image's last line)."""
+        o, N, h, w = self.moments(x)
+        L = self._b.p.latent_channels
+        if noise is None:
+            noise = torch.randn((N, L, h, w), device=x.device, dtype=torch.float32, generator=generator)
+        return ops.gaussian_sample(o, noise.to(torch.float32).contiguous(), L, self._b.p.scaling_factor if scale else 1.0)
+
+
+def encode_image(x_input: Tensor, vae: VAEEncoder, noise: Optional[Tensor] = None, generator=None) -> Tensor:
+    """PanoGenerator.py:214-225: [b, l, 3, H, W] -> sampled latents [b, l, 4, H/8, W/8] * scaling_factor (fp32)."""
+    b = x_input.shape[0]
+    z = vae.encode(x_input.flatten(0, 1), noise=noise.flatten(0, 1) if noise is not None else None, generator=generator,
+                   scale=True)
+    return z.reshape(b, -1, *z.shape[1:])
+
+
+def encode_pano(pano: Tensor, vae: VAEEncoder, latent_pad: int = 8, noise: Optional[Tensor] = None, generator=None) -> Tensor:
+    """PanFusion.py:69-71: pad the IMAGE circularly by 8 * latent_pad pixels, encode, crop latent_pad latent columns.
+    `noise` (if given) has the PADDED latent width, like the draw inside the reference's encode."""
+    return unpad_pano(encode_image(pad_pano(pano, 8 * latent_pad), vae, noise, generator), latent_pad)
 
 
 # ---- the reference's functions ---------------------------------------------------------------------------------

@@ -139,3 +139,67 @@ def test_inference_end_to_end_vs_oracle(cuda_device):
         d = np.abs(a.astype(np.int32) - b.astype(np.int32))
         print(f"[parity] inference uint8 {name}: max level diff {d.max()}, mean {d.mean():.3f}")
         assert d.mean() < 1.0 and np.percentile(d, 99) <= 4
+
+
+# ---- encoder (training step's encode_image, SURVEY.md 8f rank 4 forward half) ---------------------------------------------
+
+def test_gaussian_sample_matches_formula(cuda_device):
+    """pf_gaussian_sample == mean + exp(0.5 * clamp(logvar, -30, 20)) * eps, times the scale (diffusers
+    DiagonalGaussianDistribution.sample + PanoGenerator.py:224), incl. the clamp."""
+    from panfusion_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    N, L, h, w = 3, 4, 5, 8
+    mom = torch.randn(N * h * w, 64, generator=g) * 3
+    mom[0, L:2 * L] = torch.tensor([-50.0, 50.0, -30.0, 20.0])
+    eps = torch.randn(N, L, h, w, generator=g)
+    got = ops.gaussian_sample(mom.to(cuda_device), eps.to(cuda_device), L, 0.18215).cpu()
+    m4 = mom[:, :2 * L].reshape(N, h, w, 2 * L).permute(0, 3, 1, 2)
+    mean, logvar = m4[:, :L], m4[:, L:].clamp(-30.0, 20.0)
+    ref = (mean + torch.exp(0.5 * logvar) * eps) * 0.18215
+    torch.testing.assert_close(got, ref, rtol=2e-6, atol=1e-7)
+
+
+def _enc_cmp(name, got, ref, dtype):
+    scale = ref.abs().max().item()
+    d = (got.float().cpu() - ref).abs()
+    mx, mean = d.max().item() / scale, d.mean().item() / scale
+    # first measurement of the encoder (same blocks as the decoder, 3 stride-2 convolutions instead of up-sampling): gated
+    # at the decoder's limits x 1.5; tighten to 2x the measured value once it has been seen on hardware
+    lim = (1e-2, 1e-3) if dtype == torch.float16 else (9e-2, 7e-3)
+    print(f"[parity] {name} {dtype}: max {mx:.3e} mean {mean:.3e} (of max|ref|) limits {lim}")
+    assert mx <= lim[0] and mean <= lim[1]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("cfg_name", ["TINY_VAE_CONFIG", "SD2_VAE_CONFIG"])
+def test_vae_encode_vs_oracle(cuda_device, dtype, cfg_name):
+    """VAEEncoder on 64x64 views and a 64x128 panorama (tiny widths and the SD-2 VAE widths): the moments (mean, logvar after
+    quant_conv), the sampled + scaled latents of encode_image on the oracle's noise draw, and the circularly padded
+    panorama encode (PanoGenerator.py:214-225, PanFusion.py:66-71) against oracle/vae.py."""
+    from oracle import vae as ov
+    from panfusion_b200 import vae as pv
+    orc = ov.build_vae(getattr(ov, cfg_name))
+    enc = pv.VAEEncoder(orc, compute_dtype=dtype).prepare(cuda_device, dtype)
+    g = torch.Generator().manual_seed(4)
+    imgs = torch.rand(1, 2, 3, 64, 64, generator=g) * 2 - 1
+    pano = torch.rand(1, 1, 3, 64, 128, generator=g) * 2 - 1
+    n_img = torch.randn(2, 4, 8, 8, generator=g)
+    n_pano = torch.randn(1, 4, 8, 16 + 2 * 8, generator=g)
+    with torch.no_grad():
+        dist = orc.encode(imgs[0]).latent_dist
+        ref_z = ov.encode_image(imgs, orc, noise=n_img)
+        ref_p = ov.encode_pano(pano, orc, 8, noise=n_pano)
+    o, N, h, w = enc.moments(imgs[0].to(cuda_device))
+    mom = o[:, :8].reshape(N, h, w, 8).permute(0, 3, 1, 2)
+    _enc_cmp(f"vae.encode mean {cfg_name}", mom[:, :4], dist.mean, dtype)
+    _enc_cmp(f"vae.encode logvar {cfg_name}", mom[:, 4:], dist.logvar, dtype)
+    got_z = pv.encode_image(imgs.to(cuda_device), enc, noise=n_img.to(cuda_device)[None])
+    got_p = pv.encode_pano(pano.to(cuda_device), enc, 8, noise=n_pano.to(cuda_device)[None])
+    assert got_z.shape == ref_z.shape == (1, 2, 4, 8, 8) and got_p.shape == ref_p.shape == (1, 1, 4, 8, 16)
+    _enc_cmp(f"encode_image {cfg_name}", got_z, ref_z, dtype)
+    _enc_cmp(f"encode_pano {cfg_name}", got_p, ref_p, dtype)
+    # the reference's random draw path: runs, right shapes, different generators differ
+    from panfusion_b200.training import TrainingStep
+    g1 = torch.Generator(device=cuda_device).manual_seed(1)
+    lat, plat = TrainingStep.encode(imgs.to(cuda_device), pano.to(cuda_device), enc, 8, generator=g1)
+    assert lat.shape == (1, 2, 4, 8, 8) and plat.shape == (1, 1, 4, 8, 16) and torch.isfinite(lat).all()

@@ -174,7 +174,21 @@ def test_oracle_vae_tail_first_party_semantics():
         assert (torch.roll(img, 32, dims=-1) - rolled).abs().max() < 0.35 * img.abs().max()
     x = torch.tensor([[[[-1.0, 1.0, 0.0, -7.0, 7.0, 1 / 255]]]])  # 0.0 -> 127.5 -> 128 (half-to-even, torch.round)
     assert ov.tensor_to_image(x).tolist() == [[[[0], [255], [128], [0], [255], [128]]]]
-    assert sum(p.numel() for p in ov.build_vae().parameters()) == 49490199  # the SD VAE decoder (+ post_quant_conv)
+    full = ov.build_vae()
+    n_dec = sum(p.numel() for m in (full.decoder, full.post_quant_conv) for p in m.parameters())
+    assert n_dec == 49490199                                             # the SD VAE decoder (+ post_quant_conv)
+    assert sum(p.numel() for p in full.parameters()) == 83653863         # the whole SD AutoencoderKL (published size)
+    # encode_image / padded panorama encode (PanoGenerator.py:214-225, PanFusion.py:66-71): shapes, scaling, the draw
+    g = torch.Generator().manual_seed(1)
+    imgs = torch.rand(1, 2, 3, 64, 64, generator=g) * 2 - 1
+    noise = torch.randn(2, 4, 8, 8, generator=g)
+    with torch.no_grad():
+        dist = vae.encode(imgs[0]).latent_dist
+        z = ov.encode_image(imgs, vae, noise=noise)
+        assert z.shape == (1, 2, 4, 8, 8)
+        torch.testing.assert_close(z[0], (dist.mean + dist.std * noise) * vae.config.scaling_factor)
+        zp = ov.encode_pano(torch.rand(1, 1, 3, 64, 128, generator=g) * 2 - 1, vae, 8, generator=g)
+        assert zp.shape == (1, 1, 4, 8, 16)
 
 
 def test_py360convert_e2p_matches_reference_golden_and_scipy():
