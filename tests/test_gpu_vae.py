@@ -163,9 +163,9 @@ def _enc_cmp(name, got, ref, dtype):
     scale = ref.abs().max().item()
     d = (got.float().cpu() - ref).abs()
     mx, mean = d.max().item() / scale, d.mean().item() / scale
-    # first measurement of the encoder (same blocks as the decoder, 3 stride-2 convolutions instead of up-sampling): gated
-    # at the decoder's limits x 1.5; tighten to 2x the measured value once it has been seen on hardware
-    lim = (1e-2, 1e-3) if dtype == torch.float16 else (9e-2, 7e-3)
+    # about 2x the measured worst case over both widths (moments: fp16 1.8e-3 / 4.3e-4, bf16 2.1e-2 / 3.5e-3 of max|ref|;
+    # sampled latents 4.6e-4 / 9.3e-5 and 4.1e-3 / 7.8e-4 — profiles/pytest_gpu_r02_final.txt)
+    lim = (4e-3, 9e-4) if dtype == torch.float16 else (4.5e-2, 7e-3)
     print(f"[parity] {name} {dtype}: max {mx:.3e} mean {mean:.3e} (of max|ref|) limits {lim}")
     assert mx <= lim[0] and mean <= lim[1]
 
