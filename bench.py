@@ -441,7 +441,7 @@ def image_latency(model, inp, wl, dev, n_steps=50):
 # ------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle (a port of the reference algorithm) on the host cores
 # ------------------------------------------------------------------------------------------------------
-_ORACLE_MODEL = None
+_ORACLE_MODEL = {}
 
 
 def host_threads() -> int:
@@ -461,16 +461,18 @@ def host_threads() -> int:
     return max(1, min(n, 64))
 
 
-def _oracle_model():
+def _oracle_model(layout_cond: bool = False):
     """SD-2-size oracle model for TIMING: built on the meta device and filled by tiling one random block (the values
     do not matter for a CPU throughput baseline; PyTorch's seeded default init of 2 x 866 M parameters alone takes
-    about a minute of single-threaded RNG)."""
-    global _ORACLE_MODEL
-    if _ORACLE_MODEL is None:
-        from oracle import mvgen as om, unet as ou
+    about a minute of single-threaded RNG). layout_cond adds the panorama ControlNet of BASELINE configs[4]
+    (ControlNetModel.from_unet topology, models/pano/PanoGenerator.py:153-157)."""
+    if layout_cond not in _ORACLE_MODEL:
+        from oracle import controlnet as ocn, mvgen as om, unet as ou
         torch.set_num_threads(host_threads())
         with torch.device("meta"):
-            model = om.MultiViewBaseModel(ou.UNet2DConditionModel(**ou.SD2_CONFIG), ou.UNet2DConditionModel(**ou.SD2_CONFIG))
+            cn = ocn.ControlNetModel(ou.UNet2DConditionModel(**ou.SD2_CONFIG)) if layout_cond else None
+            model = om.MultiViewBaseModel(ou.UNet2DConditionModel(**ou.SD2_CONFIG), ou.UNet2DConditionModel(**ou.SD2_CONFIG),
+                                          pano_cn=cn)
         model = model.to_empty(device="cpu").eval()
         g = torch.Generator().manual_seed(0)
         block = torch.randn(1 << 20, generator=g) * 0.02
@@ -485,8 +487,8 @@ def _oracle_model():
                     nf = b.numel()
                     base = 2 if nf <= 80 else 5000 ** (1 / (nf / 2.5))
                     b.copy_(base ** torch.linspace(0, nf - 1, nf))
-        _ORACLE_MODEL = model
-    return _ORACLE_MODEL
+        _ORACLE_MODEL[layout_cond] = model
+    return _ORACLE_MODEL[layout_cond]
 
 
 class _OracleLoop:
@@ -497,11 +499,10 @@ class _OracleLoop:
     def __init__(self, workload):
         from oracle import sampler as osamp
         torch.set_num_threads(host_threads())
-        self.osamp, self.model = osamp, _oracle_model()
         wl = WORKLOADS[workload]
-        if wl.get("layout_cond"):
-            raise NotImplementedError("CPU arm of the layout-conditioned workload: time c2 (the ControlNet adds 7.5 % FLOPs)")
+        self.osamp, self.model = osamp, _oracle_model(bool(wl.get("layout_cond")))
         inp = synthetic_inputs(wl, 1024, "cpu", None)
+        self.cond = inp.get("pano_layout_cond")   # rolled a quarter turn per step, cumulatively (PanFusion.py:152-153)
         self.cams = inp["cams"]
         self.pano = inp["pano"]
         self.lat = osamp.init_noise(self.pano, *wl["pers_hw"], self.cams)
@@ -513,7 +514,9 @@ class _OracleLoop:
         t0 = time.perf_counter()
         self.lat, self.pano, self.cams = self.osamp.denoise_steps(
             self.model, self.lat, self.pano, self.prompt, self.pano_prompt, self.cams, num_steps=1,
-            start_step=self.i % 50)
+            start_step=self.i % 50, pano_layout_cond=self.cond)
+        if self.cond is not None:  # denoise_steps rolled its own copy for this step: keep the roll for the next call
+            self.cond = torch.roll(self.cond, self.cond.shape[-1] // 4, dims=-1)
         self.i += 1
         return time.perf_counter() - t0
 
@@ -538,10 +541,6 @@ def run_reference(args):
         return
     wl = WORKLOADS[args.workload]
     cores = host_threads()
-    if wl.get("layout_cond"):
-        print(json.dumps({"impl": "reference", "unavailable": "the CPU arm times the un-conditioned loop (workload c2); the "
-                          "layout-conditioned workload adds a ControlNet pass (+7.5 % FLOPs) that is not wired into the timing loop"}))
-        return
     loop = _OracleLoop(args.workload)
     t_warm = loop.step()
     n_timed = max(2, min(args.steps, int(args.ref_budget / max(t_warm, 1e-3))))
