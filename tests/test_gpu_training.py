@@ -20,7 +20,8 @@ def test_add_noise_bit_exact(cuda_device):
         assert torch.equal(got.cpu(), otr.add_noise(x0, eps, t, abar))
 
 
-def test_add_noise_rejects_bad_timestep(cuda_device):
+def test_add_noise_rejects_wrong_timestep_count(cuda_device):
+    """one timestep per sample is required (an out-of-table timestep traps on the device like torch raises IndexError)."""
     from panfusion_b200 import ops
     x = torch.zeros(1, 4, device=cuda_device)
     with pytest.raises(AssertionError):
